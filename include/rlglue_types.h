@@ -35,8 +35,14 @@ typedef struct {
 } reward_observation_terminal_t;
 
 /* RLStruct_util.h equivalents: the callee owns the arrays (SwimmerEnvironment.cpp:20-21,72-73). */
+#if defined(__GNUC__)
+__attribute__((visibility("default")))
+#endif
 void allocateRLStruct(rl_abstract_type_t* dst, unsigned int numInts, unsigned int numDoubles,
                       unsigned int numChars);
+#if defined(__GNUC__)
+__attribute__((visibility("default")))
+#endif
 void clearRLStruct(rl_abstract_type_t* dst);
 
 #ifdef __cplusplus

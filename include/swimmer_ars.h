@@ -1,0 +1,238 @@
+/*
+ * swimmer_ars.h -- C ABI of libswimmer_ars.so, the B200 (sm_100a) implementation of the
+ * batched Coulom swimmer + Augmented Random Search hot path.
+ *
+ * This is the drop-in boundary: plain C, pointers and sizes only (no torch / C++ types).
+ * The Python host layer (safe-exploration-with-simulator-in-rl-algorithms_b200/) binds these
+ * symbols with ctypes and mirrors the reference's Python plugin surface on top of them.
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * reference repository root).
+ *
+ * Conventions
+ *   - every `double*` / `int*` data argument is a DEVICE pointer unless it says "host";
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all calls only
+ *     enqueue work on that stream and return without synchronising;
+ *   - return value: 0 = ok, negative = swm_status (swm_strerror gives text); no exceptions
+ *     and no hidden device allocations cross this boundary;
+ *   - observation layout is the reference's: [Gdot_x, Gdot_y, th_1, thd_1, ..., th_n, thd_n]
+ *     (remy_swimmer_env.py:216-224, SwimmerEnvironment.cpp:109-116), row-major [B, 2n+2];
+ *   - a linear policy is row-major [(n-1), (2n+2)] (ars/ars_agent.py:72-73).
+ */
+#ifndef SWIMMER_ARS_H
+#define SWIMMER_ARS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SWM_API __attribute__((visibility("default")))
+#else
+#define SWM_API
+#endif
+
+#define SWM_ABI_VERSION 1
+#define SWM_MIN_SEGMENTS 2
+#define SWM_MAX_SEGMENTS 10
+
+typedef enum {
+  SWM_OK = 0,
+  SWM_ERR_BAD_ARG = -1,        /* NULL / out-of-range argument */
+  SWM_ERR_UNSUPPORTED = -2,    /* valid request this build has no kernel for */
+  SWM_ERR_CUDA = -3,           /* a CUDA runtime call failed: swm_last_cuda_error() */
+  SWM_ERR_NO_DEVICE = -4
+} swm_status;
+
+/* Dynamics variant. */
+typedef enum {
+  SWM_DYN_GYM = 0,    /* envs/gym_swimmer/swimmer/remy_swimmer_env.py:69-214: explicit Euler */
+  SWM_DYN_RLGLUE = 1  /* rlglue/environment/SwimmerEnvironment.cpp:102-271: semi-implicit Euler,
+                         literal 5n+2 system including its column/weight quirks */
+} swm_variant;
+
+/* Physical parameters of one swimmer model (host struct, passed by pointer, read during the call).
+ * Replaces SwimmerEnv.__init__ kwargs (remy_swimmer_env.py:16-29) and the RL-Glue globals
+ * n_seg,max_u,l_i,k,m_i,h_global,direction (SwimmerEnvironment.cpp:3-9). */
+typedef struct {
+  int32_t n;            /* number of segments, SWM_MIN_SEGMENTS..SWM_MAX_SEGMENTS */
+  int32_t _pad;
+  double l_i, m_i, k, h, max_u;
+  double direction[2];
+} swm_params_t;
+
+/* How each environment of a rollout obtains its action. */
+typedef enum {
+  SWM_POLICY_FIXED_ACTION = 0, /* actions[B, n-1] held constant for all H steps (BASELINE config 2) */
+  SWM_POLICY_EXPLICIT = 1,     /* policies[P, (n-1)(2n+2)], env e uses policy e / rollouts_per_policy */
+  SWM_POLICY_PHILOX = 2,       /* W +/- nu*delta_k, delta regenerated in-kernel from Philox4x32-10;
+                                  policy index q = e / rollouts_per_policy, direction k = dir0 + q/2,
+                                  sign + for even q, - for odd q  (ars_agent.py:140-142 ordering) */
+  SWM_POLICY_DELTAS = 3        /* as PHILOX but delta_k is read from deltas[D, (n-1)(2n+2)] (row q/2):
+                                  lets a caller replay the reference's own MT19937 draws */
+} swm_policy_mode;
+
+/* Distribution of the Philox perturbations. */
+typedef enum {
+  SWM_DELTA_UNIFORM_PM1 = 0, /* 2*U[0,1)-1  (ars_agent.py:137, safe_ars/ars.py:84) */
+  SWM_DELTA_UNIFORM_01 = 1   /* U[0,1)      (rlglue/agent/SwimmerAgent.py:208) */
+} swm_delta_dist;
+
+/* Philox4x32-10 addressing shared by the rollout and the update kernels (and the oracle):
+ * key = (seed lo32, seed hi32), counter = (pair j, direction k, iteration, stream);
+ * one call yields elements 2j and 2j+1 of delta_k;  u = ((a>>5)*2^26 + (b>>6)) * 2^-53. */
+typedef struct {
+  uint64_t seed;
+  uint32_t iteration;
+  uint32_t dir0;       /* global index of this shard's first direction */
+  int32_t dist;        /* swm_delta_dist */
+  int32_t _pad;
+} swm_philox_t;
+
+/* Per-step state-constraint screening (safe_ars/ars.py:111-153, Safe_ARS.isSafe/rollout) with the
+ * built-in cost of safe_ars/experiment.py:44, cost(obs) = max_i |thd_i|. */
+typedef struct {
+  int32_t enabled;
+  int32_t _pad;
+  swm_params_t sim;       /* simulator model; n must equal the real model's n */
+  double sim_thresh;      /* take the real step iff cost(sim step) <= sim_thresh */
+  double real_thresh;     /* real steps with cost > real_thresh are counted in violations[] */
+  int32_t* violations;    /* [B] or NULL */
+  int32_t* frozen_at;     /* [B] or NULL: first step index judged unsafe, H if never */
+} swm_screen_t;
+
+/* One fused H-step rollout of B environments.  Replaces Environment.rollout
+ * (ars/environment.py:37-57), Basic_ARS.rollout / Safe_ARS.rollout (safe_ars/ars.py:13-35,
+ * 124-153) and the 2N-rollout loop of ARSAgent.runOneIteration (ars/ars_agent.py:140-172). */
+typedef struct {
+  int32_t variant;              /* swm_variant */
+  int32_t policy_mode;          /* swm_policy_mode */
+  int32_t normalize;            /* 0 = ARS V1; 1 = ARS V2: action = (W diag(inv_sigma)) (obs - mean)
+                                   (ars/environment.py:31-35) */
+  int32_t clip_actions;         /* 1 = clip to +-max_u (rlglue/agent/SwimmerAgent.py:192-196) */
+  int32_t H;                    /* steps */
+  int32_t rollouts_per_policy;  /* R >= 1 consecutive envs share one policy */
+  int64_t B;                    /* number of environments */
+  const double* actions;        /* FIXED_ACTION: [B, n-1] */
+  const double* policies;       /* EXPLICIT: [B/R, (n-1)(2n+2)];  PHILOX/DELTAS: base W [(n-1)(2n+2)] */
+  const double* deltas;         /* DELTAS: [B/(2R), (n-1)(2n+2)] */
+  double nu;                    /* PHILOX/DELTAS: perturbation scale */
+  swm_philox_t philox;
+  const int32_t* dir_mask;      /* PHILOX/DELTAS, optional [B/(2R)]: directions with mask 0 are NOT
+                                   rolled out (their returns are set to NaN) -- the reward-constraint
+                                   safe exploration of ars_agent.py:144-159 */
+  const double* mean;           /* [2n+2], normalize only */
+  const double* inv_sigma;      /* [2n+2], normalize only: diag(cov)^(-1/2) */
+  const double* init_state;     /* NULL = reset() (gym: remy_swimmer_env.py:58-67; rlglue: env_start
+                                   cpp:39-42), else [B or R or 1, 2n+2] */
+  int64_t init_state_count;     /* rows in init_state: env e uses row e % init_state_count */
+  double init_perturb;          /* != 0: add init_perturb * U[0,1) to every entry of the initial state,
+                                   Philox stream 1, counter (pair j, e % R, iteration, 1): the same R
+                                   perturbed starts for every policy (declared synthetic extension for
+                                   BASELINE config 5; the reference's reset() is deterministic) */
+  double* returns;              /* [B] sum of rewards */
+  double* final_state;          /* [B, 2n+2] or NULL */
+  double* trajectory;           /* [H, B, 2n+2] time-major post-step observations, or NULL
+                                   (saved_states of ars/environment.py:53) */
+  double* stats_partial;        /* NULL, or [swm_rollout_stats_blocks(B), 2, 2n+2]: per-block
+                                   sums of (x-pivot) and (x-pivot)^2 over all visited states */
+  const double* stats_pivot;    /* [2n+2], required with stats_partial */
+  swm_screen_t screen;
+} swm_rollout_t;
+
+SWM_API int swm_abi_version(void);
+SWM_API const char* swm_strerror(int status);
+SWM_API const char* swm_last_cuda_error(void);
+SWM_API int swm_device_info(int* sm_count, int* cc_major, int* cc_minor); /* host out-pointers */
+/* sizeof() of the ABI structs in this build, so that a binding can verify its own layout */
+SWM_API int swm_abi_struct_sizes(int* params, int* philox, int* screen, int* rollout);
+
+/* Batched single step.  Replaces SwimmerEnv.step / next_observation (remy_swimmer_env.py:41-93)
+ * and updateState (SwimmerEnvironment.cpp:102-137) for B independent environments.
+ * state_out may alias state_in.  reward may be NULL. */
+SWM_API int swm_step_batched(const swm_params_t* params, int variant, const double* state_in,
+                     const double* action, double* state_out, double* reward, int64_t B,
+                     void* stream);
+
+/* Accelerations only (compute_accelerations, remy_swimmer_env.py:95-114 / cpp:139-226):
+ * acc[B, n+2] = [Gdd_x, Gdd_y, thdd_1..thdd_n]. */
+SWM_API int swm_accelerations_batched(const swm_params_t* params, int variant, const double* state,
+                              const double* action, double* acc, int64_t B, void* stream);
+
+SWM_API int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg, void* stream);
+/* number of per-block rows the rollout kernel writes into stats_partial for B envs */
+SWM_API int64_t swm_rollout_stats_blocks(const swm_params_t* params, const swm_rollout_t* cfg);
+
+/* Deterministic Welford bookkeeping for ARS V2 (replaces np.mean / np.cov over the growing
+ * saved_states list, ars/ars_agent.py:179-182).  A statistics record is
+ * [count, mean[F], M2[F]] (1+2F doubles).
+ *  - swm_stats_finalize: sums the per-block partial rows in a fixed order and converts them into a
+ *    record (count, mean, M2) -- `out_record`.  count = samples, or samples * (*units) when the
+ *    optional device int32 `units` is given (e.g. samples = 2*R*H per direction, units = the
+ *    number of directions that survived screening).
+ *  - swm_stats_merge: folds `n_records` records (contiguous, e.g. one per rank after an
+ *    all-gather, merged in index order) into `running` (Chan et al.), then writes
+ *    mean[F] and inv_sigma[F] = (M2/(count-1))^(-1/2) if those pointers are non-NULL. */
+SWM_API int swm_stats_finalize(const double* partial, int64_t n_blocks, int n_features, double samples,
+                               const int32_t* units, const double* pivot, double* out_record,
+                               void* stream);
+SWM_API int swm_stats_merge(double* running, const double* records, int n_records, int n_features,
+                    double* mean_out, double* inv_sigma_out, void* stream);
+
+/* Mean of each group of R consecutive returns (per-direction return when R rollouts share a
+ * policy; BASELINE config 5). out[B/R]. */
+SWM_API int swm_reduce_returns(const double* returns, int64_t n_groups, int R, double* out, void* stream);
+
+/* order[N]: directions sorted by max(r+_k, r-_k) descending == sort_directions
+ * (ars_agent.py:97-108, safe_ars/ars.py:37-46).  Ties: higher index first
+ * (np.argsort(kind='stable')[::-1]); NaN keys first.  returns[2N] = [r+_0, r-_0, r+_1, ...].
+ * mask (optional, [N] int32): directions with mask==0 sort after all others (screened out). */
+SWM_API int swm_ars_topb(const double* returns, const int32_t* mask, int N, int32_t* order, void* stream);
+
+/* update_policy (ars_agent.py:110-130, safe_ars/ars.py:48-65, rlglue/agent/SwimmerAgent.py:223-241):
+ *   used    = order[0 .. n_order)            (order == NULL: identity, i.e. index order)
+ *             if mask != NULL: only the first min(n_order, #mask!=0) entries (order must come from
+ *             swm_ars_topb with the same mask, which sorts screened-out directions last)
+ *   sigma_R = std of the 2*|used| returns with `ddof` (0: np.std, 1: statistics.stdev)
+ *   W      += alpha * ( sum_{k in used} (r+_k - r-_k) delta_k / (divisor * sigma_R) )
+ *             divisor <= 0 means |used| (safe_ars/ars.py:64 len(order)); ars_agent.py:128 passes b.
+ * The three reference semantics are therefore
+ *   ars/ars_agent.py   : n_order = N, divisor = b, ddof = 0      (sorts, then uses ALL directions)
+ *   safe_ars/ars.py    : n_order = b, divisor = 0 (=b), ddof = 0 (true top-b)
+ *   rlglue agent       : order = NULL, n_order = b, divisor = b, ddof = 1
+ * delta_k is regenerated from Philox (deltas == NULL; direction index dir0 + k) or read from
+ * deltas[N, wsize].  If nothing is used W is unchanged (ars_agent.py:174).  sigma_out: optional
+ * device double. */
+SWM_API int swm_ars_update(double* W, int wsize, const double* returns, int N, const int32_t* order,
+                           int n_order, const int32_t* mask, double divisor, int ddof, double alpha,
+                           const swm_philox_t* philox, const double* deltas, double* sigma_out,
+                           void* stream);
+
+/* mask[k] = (sim_returns[2k] > threshold) && (sim_returns[2k+1] > threshold): the screening rule of
+ * ars_agent.py:150-157 (a direction is rolled out in the real world only if both simulated
+ * returns exceed the simulator threshold).  n_pass: optional device int32 = number of survivors. */
+SWM_API int swm_screen_mask(const double* sim_returns, int N, double threshold, int32_t* mask,
+                            int32_t* n_pass, void* stream);
+
+/* select_action for a batch (ars/environment.py:19-35): actions[B, n-1] = W_e obs_e (V1) or
+ * (W_e diag(inv_sigma)) (obs_e - mean) (V2); env e uses policy e / rollouts_per_policy of
+ * policies[P, (n-1)(2n+2)].  clip != 0 clips to +-max_u. */
+SWM_API int swm_policy_actions(const swm_params_t* params, const double* obs, const double* policies,
+                               int rollouts_per_policy, const double* mean, const double* inv_sigma,
+                               int clip, double* actions, int64_t B, void* stream);
+
+/* Writes delta_k (k = dir0 .. dir0+count-1) into out[count, wsize]: lets tests and the host API
+ * see exactly the perturbations the kernels use. */
+SWM_API int swm_philox_deltas(const swm_philox_t* philox, int count, int wsize, double* out, void* stream);
+
+/* FP64 pipe probe: every thread runs `iters` x 8 independent DFMA chains; returns through
+ * *flops_out (host) the number of floating-point operations executed (2 per DFMA).  Used by
+ * bench.py to measure the FP64 roofline denominator on the box (MEASURED_PEAKS.json has none). */
+SWM_API int swm_fp64_probe(int blocks, int threads, int iters, double* sink, double* flops_out,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWIMMER_ARS_H */

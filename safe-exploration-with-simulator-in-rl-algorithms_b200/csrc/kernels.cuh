@@ -1,0 +1,339 @@
+// Batched step kernel and the persistent fused H-step rollout kernel.
+// One thread owns one environment; the state (2n+2 doubles), its sines/cosines and (for
+// n <= 5) the environment's own perturbed policy live in registers for the whole rollout.
+// Nothing but the final return (8 B/env), optional final state and optional trajectory is
+// written to HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/swimmer_ars.h"
+#include "dynamics.cuh"
+#include "philox.cuh"
+
+namespace swm {
+
+constexpr int kStepBlock = 128;
+constexpr int kRolloutBlock = 64;  // threads per CTA of the rollout kernel (2 warps)
+
+// Where the per-environment policy lives during a rollout.
+enum WMode {
+  W_NONE = 0,        // fixed actions
+  W_REG = 1,         // registers (n <= 5: at most 48 doubles)
+  W_SMEM_THREAD = 2, // shared memory, one column per thread: sW[e * BLOCK + tid]
+  W_SMEM_GROUP = 3   // shared memory, one copy per warp (rollouts_per_policy % 32 == 0): broadcast
+};
+
+struct RolloutArgs {
+  Phys real;
+  Phys sim;  // screening model
+  int H;
+  int R;  // rollouts per policy
+  int policy_mode;
+  int clip;
+  long long B;
+  const double* actions;
+  const double* policies;
+  const double* deltas;
+  const int* dir_mask;
+  double nu;
+  double init_perturb;
+  unsigned long long seed;
+  unsigned int iteration, dir0;
+  int dist;
+  const double* mean;
+  const double* inv_sigma;
+  const double* init_state;
+  long long init_count;
+  double* returns;
+  double* final_state;
+  double* trajectory;
+  double* stats_partial;
+  const double* stats_pivot;
+  double sim_thresh, real_thresh;
+  int* violations;
+  int* frozen_at;
+};
+
+// ---------------------------------------------------------------------------------------------
+// step / accelerations
+// ---------------------------------------------------------------------------------------------
+template <int N, int VARIANT, bool ACC_ONLY>
+__global__ void __launch_bounds__(kStepBlock)
+step_kernel(Phys P, const double* __restrict__ state_in, const double* __restrict__ action,
+            double* __restrict__ state_out, double* __restrict__ reward, long long B) {
+  constexpr int NO = 2 * N + 2, NA = N - 1;
+  const long long e = (long long)blockIdx.x * kStepBlock + threadIdx.x;
+  if (e >= B) return;
+  const double2* sp = reinterpret_cast<const double2*>(state_in + e * NO);
+  double gdx, gdy, th[N], thd[N], u[NA > 0 ? NA : 1];
+  {
+    const double2 g = sp[0];
+    gdx = g.x; gdy = g.y;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const double2 v = sp[1 + i]; th[i] = v.x; thd[i] = v.y; }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) u[a] = action[e * NA + a];
+  }
+  if (ACC_ONLY) {
+    double s[N], c[N], gddx, gddy, thdd[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) sincos(th[i], &s[i], &c[i]);
+    if (VARIANT == 0) gym_accelerations<N>(P, s, c, gdx, gdy, thd, u, gddx, gddy, thdd);
+    else rlglue_accelerations<N>(P, s, c, gdx, gdy, thd, u, gddx, gddy, thdd);
+    double* o = state_out + e * (N + 2);
+    o[0] = gddx; o[1] = gddy;
+#pragma unroll
+    for (int i = 0; i < N; ++i) o[2 + i] = thdd[i];
+    return;
+  }
+  const double r = swimmer_step<N, VARIANT>(P, gdx, gdy, th, thd, u);
+  double2* op = reinterpret_cast<double2*>(state_out + e * NO);
+  op[0] = make_double2(gdx, gdy);
+#pragma unroll
+  for (int i = 0; i < N; ++i) op[1 + i] = make_double2(th[i], thd[i]);
+  if (reward) reward[e] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused rollout
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ double cost_max_abs_thd(const double (&thd)[N]) {
+  // safe_ars/experiment.py:44  np.max(|obs[3+2i]|); NaN propagates like np.max
+  double cst = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double a = fabs(thd[i]);
+    cst = (a > cst || a != a) ? a : cst;
+  }
+  return cst;
+}
+
+// LINEAR: 0 fixed actions, 1 linear policy.  NORM: ARS V2 normalisation.  STATS: accumulate
+// shifted first/second moments of every visited state.  SCREEN: per-step simulator screening.
+template <int N, int VARIANT, int WMODE, bool NORM, bool STATS, bool SCREEN>
+__global__ void __launch_bounds__(kRolloutBlock)
+rollout_kernel(const RolloutArgs a) {
+  constexpr int NO = 2 * N + 2, NA = N - 1, WS = NA * NO;
+  constexpr bool LINEAR = (WMODE != W_NONE);
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const long long e0 = (long long)blockIdx.x * kRolloutBlock + tid;
+  const bool active = e0 < a.B;
+  const long long e = active ? e0 : a.B - 1;  // idle lanes shadow the last env, never store
+
+  // ---- initial state ----
+  double gdx, gdy, th[N], thd[N];
+  if (a.init_state) {
+    const double* sp = a.init_state + (e % a.init_count) * NO;
+    gdx = sp[0]; gdy = sp[1];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { th[i] = sp[2 + 2 * i]; thd[i] = sp[3 + 2 * i]; }
+  } else if (VARIANT == 0) {
+    gdx = gdy = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { th[i] = 1.5707963267948966; thd[i] = 0.0; }
+  } else {
+    gdx = gdy = 0.001;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { th[i] = 0.001; thd[i] = 0.001; }
+  }
+
+  if (a.init_perturb != 0.0) {
+    // declared synthetic extension (BASELINE config 5): start = init + init_perturb * U[0,1),
+    // Philox stream 1 keyed by the rollout index within the policy, so that every policy sees the
+    // same R perturbed starts (common random numbers for the +/- pairs).
+    const unsigned int r = (unsigned int)(e % a.R);
+#pragma unroll
+    for (int j = 0; j < NO; j += 2) {
+      double d0, d1;
+      philox_delta_pair(a.seed, a.iteration, r, 1u, (uint32_t)(j >> 1), SWM_DELTA_UNIFORM_01, d0, d1);
+      if (j == 0) { gdx = fma(a.init_perturb, d0, gdx); gdy = fma(a.init_perturb, d1, gdy); }
+      else { th[(j - 2) / 2] = fma(a.init_perturb, d0, th[(j - 2) / 2]);
+             thd[(j - 2) / 2] = fma(a.init_perturb, d1, thd[(j - 2) / 2]); }
+    }
+  }
+
+  // ---- policy ----
+  double Wr[WMODE == W_REG ? WS : 1];
+  double u[NA > 0 ? NA : 1];
+  double mu[NORM ? NO : 1];
+  double* sW = nullptr;  // W_SMEM_*: element j of this thread's policy at sW[j * wstride]
+  int wstride = 1;
+  if (WMODE == W_SMEM_THREAD) { sW = smem + tid; wstride = kRolloutBlock; }
+  if (WMODE == W_SMEM_GROUP) { sW = smem + (tid >> 5) * WS; wstride = 1; }
+  if (LINEAR) {
+    const long long q = e / a.R;  // policy index
+    const bool philox = a.policy_mode == SWM_POLICY_PHILOX;
+    const bool from_mem = a.policy_mode == SWM_POLICY_DELTAS;
+    const double* base = (philox || from_mem) ? a.policies : a.policies + q * WS;
+    const double* dmem = from_mem ? a.deltas + (q >> 1) * WS : nullptr;
+    const double sgn_nu = (q & 1) ? -a.nu : a.nu;
+    const unsigned int dir = a.dir0 + (unsigned int)(q >> 1);
+    const bool writer = (WMODE != W_SMEM_GROUP) || ((tid & 31) == 0);
+    auto make_pair = [&](int j, double& w0, double& w1) {
+      w0 = base[j];
+      w1 = (j + 1 < WS) ? base[j + 1] : 0.0;
+      if (philox || from_mem) {
+        double d0, d1 = 0.0;
+        if (philox) {
+          philox_delta_pair(a.seed, a.iteration, dir, 0u, (uint32_t)(j >> 1), a.dist, d0, d1);
+        } else {
+          d0 = dmem[j];
+          if (j + 1 < WS) d1 = dmem[j + 1];
+        }
+        // policy +- nu*delta exactly as ars_agent.py:141-142 (product rounded, then added)
+        w0 = __dadd_rn(w0, __dmul_rn(sgn_nu, d0));
+        w1 = __dadd_rn(w1, __dmul_rn(sgn_nu, d1));
+      }
+      if (NORM) {  // policy @ diag(cov^-1/2), ars/environment.py:32-33
+        w0 *= a.inv_sigma[j % NO];
+        if (j + 1 < WS) w1 *= a.inv_sigma[(j + 1) % NO];
+      }
+    };
+    if (WMODE == W_REG) {
+#pragma unroll
+      for (int j = 0; j < WS; j += 2) {
+        double w0, w1;
+        make_pair(j, w0, w1);
+        Wr[j] = w0;
+        if (j + 1 < WS) Wr[j + 1] = w1;
+      }
+    } else if (writer) {
+#pragma unroll 1
+      for (int j = 0; j < WS; j += 2) {
+        double w0, w1;
+        make_pair(j, w0, w1);
+        sW[j * wstride] = w0;
+        if (j + 1 < WS) sW[(j + 1) * wstride] = w1;
+      }
+    }
+    if (NORM) {
+#pragma unroll
+      for (int j = 0; j < NO; ++j) mu[j] = a.mean[j];
+    }
+    if (WMODE == W_SMEM_GROUP) __syncwarp();
+  } else {
+#pragma unroll
+    for (int k = 0; k < NA; ++k) u[k] = a.actions[e * NA + k];
+  }
+
+  double s1[STATS ? NO : 1], s2[STATS ? NO : 1], piv[STATS ? NO : 1];
+  if (STATS) {
+#pragma unroll
+    for (int j = 0; j < NO; ++j) { s1[j] = 0.0; s2[j] = 0.0; piv[j] = a.stats_pivot[j]; }
+  }
+
+  // reward-constraint safe exploration (ars_agent.py:144-159): a screened-out direction is never
+  // rolled out in the real world; its returns are NaN and it contributes no statistics.
+  bool skipped = false;
+  if (LINEAR && a.dir_mask) skipped = a.dir_mask[(e / a.R) >> 1] == 0;
+  const int steps = skipped ? 0 : a.H;
+
+  double ret = skipped ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
+  int viol = 0, frozen = a.H;
+  double* traj = a.trajectory ? a.trajectory + e * NO : nullptr;
+  const long long traj_step = a.B * NO;
+
+  for (int t = 0; t < steps; ++t) {
+    if (LINEAR) {
+      double obs[NO];
+      obs[0] = gdx; obs[1] = gdy;
+#pragma unroll
+      for (int i = 0; i < N; ++i) { obs[2 + 2 * i] = th[i]; obs[3 + 2 * i] = thd[i]; }
+      if (NORM) {
+#pragma unroll
+        for (int j = 0; j < NO; ++j) obs[j] -= mu[j];
+      }
+#pragma unroll
+      for (int k = 0; k < NA; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < NO; ++j) {
+          const double w = (WMODE == W_REG) ? Wr[k * NO + j] : sW[(k * NO + j) * wstride];
+          acc = fma(w, obs[j], acc);
+        }
+        if (a.clip) acc = fmin(fmax(acc, -a.real.max_u), a.real.max_u);
+        u[k] = acc;
+      }
+    }
+    if (SCREEN) {
+      // Safe_ARS.isSafe (safe_ars/ars.py:111-122): one simulator step from the current state
+      double sgx = gdx, sgy = gdy, sth[N], sthd[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) { sth[i] = th[i]; sthd[i] = thd[i]; }
+      swimmer_step<N, 0>(a.sim, sgx, sgy, sth, sthd, u);
+      if (!(cost_max_abs_thd<N>(sthd) <= a.sim_thresh)) {
+        // unsafe: nothing advances, and since obs and policy never change it never will again
+        // (safe_ars/ars.py:151-152) -- the remaining H-t steps are this state repeated.
+        frozen = t;
+        if (traj && active) {
+          for (int tt = t; tt < a.H; ++tt) {
+            double* o = traj + (long long)tt * traj_step;
+            o[0] = gdx; o[1] = gdy;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { o[2 + 2 * i] = th[i]; o[3 + 2 * i] = thd[i]; }
+          }
+        }
+        break;
+      }
+    }
+    ret += swimmer_step<N, VARIANT>(a.real, gdx, gdy, th, thd, u);
+    if (SCREEN) viol += (cost_max_abs_thd<N>(thd) > a.real_thresh) ? 1 : 0;
+    if (STATS) {
+      double d;
+      d = gdx - piv[0]; s1[0] += d; s2[0] = fma(d, d, s2[0]);
+      d = gdy - piv[1]; s1[1] += d; s2[1] = fma(d, d, s2[1]);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        d = th[i] - piv[2 + 2 * i]; s1[2 + 2 * i] += d; s2[2 + 2 * i] = fma(d, d, s2[2 + 2 * i]);
+        d = thd[i] - piv[3 + 2 * i]; s1[3 + 2 * i] += d; s2[3 + 2 * i] = fma(d, d, s2[3 + 2 * i]);
+      }
+    }
+    if (traj && active) {
+      double2* o = reinterpret_cast<double2*>(traj + (long long)t * traj_step);
+      o[0] = make_double2(gdx, gdy);
+#pragma unroll
+      for (int i = 0; i < N; ++i) o[1 + i] = make_double2(th[i], thd[i]);
+    }
+  }
+
+  if (active) {
+    a.returns[e] = ret;
+    if (a.final_state) {
+      double2* o = reinterpret_cast<double2*>(a.final_state + e * NO);
+      o[0] = make_double2(gdx, gdy);
+#pragma unroll
+      for (int i = 0; i < N; ++i) o[1 + i] = make_double2(th[i], thd[i]);
+    }
+    if (SCREEN) {
+      if (a.violations) a.violations[e] = viol;
+      if (a.frozen_at) a.frozen_at[e] = frozen;
+    }
+  }
+
+  if (STATS) {
+    // fixed-order block reduction: lanes by xor-butterfly, then warps in index order
+    __shared__ double red[kRolloutBlock / 32][2 * NO];
+#pragma unroll
+    for (int j = 0; j < NO; ++j) {
+      double v1 = active ? s1[j] : 0.0, v2 = active ? s2[j] : 0.0;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, off);
+      }
+      if ((tid & 31) == 0) { red[tid >> 5][j] = v1; red[tid >> 5][NO + j] = v2; }
+    }
+    __syncthreads();
+    if (tid < 2 * NO) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kRolloutBlock / 32; ++w) v += red[w][tid];
+      a.stats_partial[(long long)blockIdx.x * 2 * NO + tid] = v;
+    }
+  }
+}
+
+}  // namespace swm

@@ -1,0 +1,165 @@
+"""Device-resident ARS iteration: the batched replacement of the sequential loop in
+ARSAgent.runOneIteration (ars/ars_agent.py:132-185) and Basic_ARS.train (safe_ars/ars.py:82-97).
+
+One iteration =
+  1. [reward-constraint safe mode] 2N simulator rollouts -> screening mask        (swm_rollout, swm_screen_mask)
+  2. 2N (x R) real rollouts, all in one fused kernel launch                        (swm_rollout)
+  3. [R > 1] per-direction mean return; [V2] per-rank moment record                (swm_reduce_returns, swm_stats_finalize)
+  4. [world > 1] ONE all-gather of the packed per-rank record over NCCL            (torch.distributed)
+  5. redundantly on every rank, bit-identically: top-b ranking, delta-weighted
+     update with deltas regenerated from Philox, Welford merge in rank order       (swm_ars_topb, swm_ars_update, swm_stats_merge)
+
+Directions are sharded contiguously across ranks (rank r owns [r N/world, (r+1) N/world)); the
+delta tensors never move.  Nothing in an iteration synchronises with the host.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from ._lib import ARS_AGENT, DELTA_PM1, GYM
+
+
+class ArsEngine:
+    def __init__(self, params, *, N, b, alpha, nu, H, v2=False, semantics=ARS_AGENT,
+                 rollouts_per_direction=1, seed=0, variant=GYM, delta_dist=DELTA_PM1,
+                 clip_actions=False, init_perturb=0.0, initial_policy=None, group=None,
+                 distributed=None, device=None, sim_params=None, sim_threshold=None,
+                 step_screen=None):
+        _lib.require_cuda()
+        self.params, self.N, self.b, self.alpha, self.nu, self.H = params, int(N), int(b), alpha, nu, int(H)
+        self.v2, self.semantics, self.R = bool(v2), semantics, int(rollouts_per_direction)
+        self.seed = 0 if seed is None else int(seed)
+        self.variant, self.delta_dist, self.clip = variant, delta_dist, clip_actions
+        self.init_perturb = float(init_perturb)
+        self.device = torch.device(device) if device is not None else torch.device(
+            "cuda", torch.cuda.current_device())
+        self.group = group
+        use_dist = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        self.world = dist.get_world_size(group) if use_dist else 1
+        self.rank = dist.get_rank(group) if use_dist else 0
+        if self.N % self.world != 0:
+            raise ValueError("N=%d directions do not shard over %d ranks" % (self.N, self.world))
+        self.N_local = self.N // self.world
+        self.dir0 = self.rank * self.N_local
+        n = params.n
+        self.no, self.ws = ops.obs_dim(n), ops.policy_size(n)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.W = torch.zeros(self.ws, **f64)
+        if initial_policy is not None:
+            self.W.copy_(torch.as_tensor(initial_policy, dtype=torch.float64).reshape(-1))
+        self.iteration = 0
+        # V2 running statistics: record = [count, mean[F], M2[F]]; mean=0 / sigma=1 until the first
+        # update (ars_agent.py:87-90)
+        self.stats = torch.zeros(1 + 2 * self.no, **f64)
+        self.mean = torch.zeros(self.no, **f64)
+        self.inv_sigma = torch.ones(self.no, **f64)
+        self.pivot = ops.reset_state(n, variant, self.device)
+        # reward-constraint screening through a simulator model (ars_agent.py:144-157)
+        self.sim_params, self.sim_threshold = sim_params, sim_threshold
+        # per-step state-constraint screening (safe_ars/ars.py:124-153)
+        self.step_screen = step_screen
+        # persistent buffers: the iteration loop allocates nothing
+        Bl = 2 * self.N_local * self.R
+        self.B_local = Bl
+        self._out = {"returns": torch.empty(Bl, **f64)}
+        self._sim_out = {"returns": torch.empty(Bl, **f64)} if sim_params is not None else None
+        self.rec_len = 2 * self.N_local + 1 + 2 * self.no
+        self._record = torch.zeros(self.rec_len, **f64)
+        self._gathered = torch.zeros(self.world * self.rec_len, **f64)
+        self.returns = torch.zeros(2 * self.N, **f64)        # last iteration, all ranks
+        self._records = torch.zeros(self.world, 1 + 2 * self.no, **f64)
+        self.order = torch.zeros(self.N, dtype=torch.int32, device=self.device)
+        self.sigma = torch.zeros(1, **f64)
+        self.mask = None
+        if sim_params is not None:
+            self.mask_local = torch.ones(self.N_local, dtype=torch.int32, device=self.device)
+            self.n_pass_local = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.mask = torch.ones(self.N, dtype=torch.int32, device=self.device)
+            self.sim_returns = torch.zeros(Bl, **f64)
+        self.last = None
+
+    # -------------------------------------------------------------------------------------------
+    def _rollouts(self, params, out, deltas_local, dir_mask, want_stats, want_trajectory, screen):
+        return ops.rollout(
+            params, self.H, B=self.B_local, variant=self.variant, base_policy=self.W, nu=self.nu,
+            deltas=deltas_local, dir_mask=dir_mask, init_perturb=self.init_perturb, seed=self.seed,
+            iteration=self.iteration, dir0=self.dir0, delta_dist=self.delta_dist,
+            rollouts_per_policy=self.R, mean=self.mean if self.v2 else None,
+            inv_sigma=self.inv_sigma if self.v2 else None, clip_actions=self.clip,
+            stats_pivot=self.pivot if want_stats else None, want_trajectory=want_trajectory,
+            screen=screen, out=out)
+
+    def run_iteration(self, deltas=None, want_trajectory=False, update=True):
+        """One ARS iteration.  `deltas` ([N, ws] device tensor): use these perturbations instead of
+        Philox (replaying the reference's numpy draws).  Returns the device tensor of all 2N
+        per-policy returns (NaN for screened-out directions); never synchronises."""
+        Nl, R = self.N_local, self.R
+        deltas_local = None if deltas is None else deltas.reshape(self.N, self.ws)[self.dir0:self.dir0 + Nl]
+        dir_mask = None
+        if self.sim_params is not None:
+            sim = self._rollouts(self.sim_params, self._sim_out, deltas_local, None, False, False, None)
+            sim_ret = sim.returns if R == 1 else ops.reduce_returns(sim.returns, R)
+            self.sim_returns = sim_ret
+            ops.screen_mask(sim_ret, self.sim_threshold, self.mask_local, self.n_pass_local)
+            dir_mask = self.mask_local
+        res = self._rollouts(self.params, self._out, deltas_local, dir_mask, self.v2, want_trajectory,
+                             self.step_screen)
+        self.last = res
+        rec = self._record
+        if R == 1:
+            rec[:2 * Nl].copy_(res.returns)
+        else:
+            ops.reduce_returns(res.returns, R, out=rec[:2 * Nl])
+        if self.v2:
+            units = self.n_pass_local if dir_mask is not None else None
+            samples = float(2 * R * self.H) if units is not None else res.samples
+            ops.stats_finalize(res.stats_partial, samples, self.pivot, out=rec[2 * Nl:], units=units)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._gathered, rec, group=self.group)
+            g = self._gathered.view(self.world, self.rec_len)
+            self.returns.view(self.world, 2 * Nl).copy_(g[:, :2 * Nl])
+            self._records.copy_(g[:, 2 * Nl:])
+            if self.mask is not None:
+                self.mask.copy_((~torch.isnan(self.returns.view(self.N, 2)[:, 0])).to(torch.int32))
+        else:
+            self.returns.copy_(rec[:2 * Nl])
+            self._records[0].copy_(rec[2 * Nl:])
+            if self.mask is not None:
+                self.mask.copy_(self.mask_local)
+        if update:
+            self.apply_update(deltas)
+        return self.returns
+
+    def apply_update(self, deltas=None):
+        use_order, n_order, divisor, ddof = ops.update_args(self.semantics, self.N, self.b)
+        order = None
+        if use_order:
+            order = ops.ars_topb(self.returns, self.mask, out=self.order)
+        ops.ars_update(self.W, self.returns, self.N, order=order, n_order=n_order, divisor=divisor,
+                       ddof=ddof, alpha=self.alpha, seed=self.seed, iteration=self.iteration, dir0=0,
+                       delta_dist=self.delta_dist, deltas=deltas, mask=self.mask if use_order else None,
+                       sigma_out=self.sigma)
+        if self.v2:
+            ops.stats_merge(self.stats, self._records, self.mean, self.inv_sigma)
+        self.iteration += 1
+
+    # ---- host views ----
+    def policy_numpy(self):
+        n = self.params.n
+        return self.W.cpu().numpy().reshape(n - 1, 2 * n + 2).copy()
+
+    def set_policy(self, W):
+        self.W.copy_(torch.as_tensor(W, dtype=torch.float64).reshape(-1))
+
+    def state_dict(self):
+        """Everything needed to resume bit-exactly: policy, Philox position, V2 statistics."""
+        return {"W": self.W.cpu().numpy(), "iteration": self.iteration, "seed": self.seed,
+                "stats": self.stats.cpu().numpy(), "mean": self.mean.cpu().numpy(),
+                "inv_sigma": self.inv_sigma.cpu().numpy()}
+
+    def load_state_dict(self, sd):
+        self.W.copy_(torch.as_tensor(sd["W"]))
+        self.iteration, self.seed = int(sd["iteration"]), int(sd["seed"])
+        self.stats.copy_(torch.as_tensor(sd["stats"]))
+        self.mean.copy_(torch.as_tensor(sd["mean"]))
+        self.inv_sigma.copy_(torch.as_tensor(sd["inv_sigma"]))

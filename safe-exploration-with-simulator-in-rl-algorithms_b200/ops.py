@@ -1,0 +1,329 @@
+"""Tensor-level wrappers over the C ABI (include/swimmer_ars.h).
+
+Every function takes/returns CUDA float64 tensors, enqueues on torch's current stream and does
+not synchronise.  These are the batched entry points the reference lacks
+(`step_batched(actions[B])`, fused rollouts, the ARS update); the reference-shaped classes in
+swimmer_env.py / environment.py / ars_agent.py / safe_ars.py are thin layers over them.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (ARS_AGENT, ARS_RLGLUE, ARS_TOPB, DELTA_01, DELTA_PM1, GYM, POLICY_DELTAS,
+                   POLICY_EXPLICIT, POLICY_FIXED_ACTION, POLICY_PHILOX, RLGLUE)
+
+__all__ = ["step_batched", "accelerations_batched", "rollout", "RolloutResult", "philox_deltas",
+           "ars_topb", "ars_update", "stats_finalize", "stats_merge", "reduce_returns", "screen_mask", "policy_actions", "update_args",
+           "fp64_probe", "obs_dim", "act_dim", "policy_size", "reset_state"]
+
+
+def obs_dim(n):
+    return 2 * n + 2
+
+
+def act_dim(n):
+    return n - 1
+
+
+def policy_size(n):
+    return (n - 1) * (2 * n + 2)
+
+
+def reset_state(n, variant=GYM, device="cuda"):
+    """reset() of remy_swimmer_env.py:58-67 (gym) or env_start of SwimmerEnvironment.cpp:39-42."""
+    s = torch.zeros(2 * n + 2, dtype=torch.float64, device=device)
+    if variant == GYM:
+        s[2::2] = 1.5707963267948966
+    else:
+        s[:] = 0.001
+    return s
+
+
+def _dev(t):
+    return t.device if t is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+def step_batched(params, states, actions, variant=GYM, out=None, want_reward=True):
+    """states[B, 2n+2], actions[B, n-1] -> (next_states[B, 2n+2], rewards[B])."""
+    _lib.require_cuda()
+    n = params.n
+    B = states.shape[0]
+    _lib.f64(states, (B, obs_dim(n)))
+    _lib.f64(actions, (B, act_dim(n)))
+    states, actions = states.contiguous(), actions.contiguous()
+    out = torch.empty_like(states) if out is None else out
+    rew = torch.empty(B, dtype=torch.float64, device=states.device) if want_reward else None
+    with torch.cuda.device(states.device):
+        _lib.check(_lib.lib().swm_step_batched(ctypes.byref(params), variant, _lib.ptr(states),
+                                               _lib.ptr(actions), _lib.ptr(out), _lib.ptr(rew), B,
+                                               _lib.stream_ptr()))
+    return out, rew
+
+
+def accelerations_batched(params, states, actions, variant=GYM):
+    """-> acc[B, n+2] = [Gdd_x, Gdd_y, thdd_1..n] (compute_accelerations)."""
+    _lib.require_cuda()
+    n = params.n
+    B = states.shape[0]
+    _lib.f64(states, (B, obs_dim(n)))
+    _lib.f64(actions, (B, act_dim(n)))
+    states, actions = states.contiguous(), actions.contiguous()
+    acc = torch.empty(B, n + 2, dtype=torch.float64, device=states.device)
+    with torch.cuda.device(states.device):
+        _lib.check(_lib.lib().swm_accelerations_batched(ctypes.byref(params), variant,
+                                                        _lib.ptr(states), _lib.ptr(actions),
+                                                        _lib.ptr(acc), B, _lib.stream_ptr()))
+    return acc
+
+
+class RolloutResult:
+    __slots__ = ("returns", "final_state", "trajectory", "stats_partial", "stats_blocks",
+                 "violations", "frozen_at", "samples")
+
+    def __init__(self):
+        for s in self.__slots__:
+            setattr(self, s, None)
+
+
+def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base_policy=None, nu=0.0,
+            deltas=None, dir_mask=None, init_perturb=0.0,
+            seed=0, iteration=0, dir0=0, delta_dist=DELTA_PM1, rollouts_per_policy=1, mean=None,
+            inv_sigma=None, clip_actions=False, init_state=None, want_final=False,
+            want_trajectory=False, stats_pivot=None, screen=None, out=None, device=None):
+    """One fused H-step rollout of B environments (swm_rollout).
+
+    Exactly one of
+      actions[B, n-1]                  fixed actions (BASELINE config 2),
+      policies[P, n-1, 2n+2]           explicit policies, env e uses policy e // rollouts_per_policy,
+      base_policy[n-1, 2n+2] (+ nu, seed, iteration, dir0): W +- nu*delta_k from in-kernel Philox,
+                                       B = 2 * n_directions * rollouts_per_policy
+                                       (+ deltas[D, n-1, 2n+2]: read delta_k from memory instead)
+    dir_mask[D] int32 (base_policy modes): directions with 0 are not rolled out (returns NaN).
+    screen = dict(sim_params=..., sim_thresh=..., real_thresh=...) enables Safe_ARS screening.
+    stats_pivot[2n+2] enables the V2 moment accumulation.  `out` may carry preallocated
+    tensors (returns, final_state, trajectory, stats_partial) to stay allocation-free in loops.
+    """
+    _lib.require_cuda()
+    n = params.n
+    no, na, ws = obs_dim(n), act_dim(n), policy_size(n)
+    cfg = _lib.SwmRollout()
+    keep = []  # keep contiguous temporaries alive until the launch is enqueued
+    if actions is not None:
+        actions = _lib.f64(actions).contiguous()
+        B = actions.shape[0] if B is None else B
+        assert tuple(actions.shape) == (B, na)
+        cfg.policy_mode, cfg.actions = POLICY_FIXED_ACTION, actions.data_ptr()
+        dev = actions.device
+        keep.append(actions)
+    elif policies is not None:
+        policies = _lib.f64(policies).contiguous().reshape(-1, ws)
+        P = policies.shape[0]
+        B = P * rollouts_per_policy if B is None else B
+        assert B == P * rollouts_per_policy
+        cfg.policy_mode, cfg.policies = POLICY_EXPLICIT, policies.data_ptr()
+        dev = policies.device
+        keep.append(policies)
+    elif base_policy is not None:
+        base_policy = _lib.f64(base_policy).contiguous().reshape(-1)
+        assert base_policy.numel() == ws and B is not None
+        cfg.policy_mode, cfg.policies = POLICY_PHILOX, base_policy.data_ptr()
+        dev = base_policy.device
+        keep.append(base_policy)
+        if deltas is not None:
+            deltas = _lib.f64(deltas).contiguous().reshape(-1, ws)
+            assert deltas.shape[0] * 2 * rollouts_per_policy == B
+            cfg.policy_mode, cfg.deltas = POLICY_DELTAS, deltas.data_ptr()
+            keep.append(deltas)
+        if dir_mask is not None:
+            assert dir_mask.dtype == torch.int32 and dir_mask.is_contiguous()
+            assert dir_mask.numel() * 2 * rollouts_per_policy == B
+            cfg.dir_mask = dir_mask.data_ptr()
+    else:
+        raise ValueError("one of actions / policies / base_policy is required")
+    if device is not None:
+        dev = torch.device(device)
+    cfg.variant, cfg.H, cfg.B = variant, int(H), int(B)
+    cfg.rollouts_per_policy = int(rollouts_per_policy)
+    cfg.clip_actions = int(bool(clip_actions))
+    cfg.nu = float(nu)
+    cfg.init_perturb = float(init_perturb)
+    cfg.philox.seed, cfg.philox.iteration = int(seed) & (2 ** 64 - 1), int(iteration)
+    cfg.philox.dir0, cfg.philox.dist = int(dir0), int(delta_dist)
+    if (mean is None) != (inv_sigma is None):
+        raise ValueError("mean and inv_sigma go together")
+    if mean is not None:
+        mean = _lib.f64(mean, (no,)).contiguous()
+        inv_sigma = _lib.f64(inv_sigma, (no,)).contiguous()
+        cfg.normalize, cfg.mean, cfg.inv_sigma = 1, mean.data_ptr(), inv_sigma.data_ptr()
+        keep += [mean, inv_sigma]
+    if init_state is not None:
+        init_state = _lib.f64(init_state).contiguous().reshape(-1, no)
+        cfg.init_state, cfg.init_state_count = init_state.data_ptr(), init_state.shape[0]
+        keep.append(init_state)
+    res = RolloutResult()
+    out = out or {}
+
+    def buf(name, shape, dtype=torch.float64):
+        t = out.get(name)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+        assert tuple(t.shape) == tuple(shape) and t.is_contiguous()
+        return t
+
+    res.returns = buf("returns", (B,))
+    cfg.returns = res.returns.data_ptr()
+    if want_final:
+        res.final_state = buf("final_state", (B, no))
+        cfg.final_state = res.final_state.data_ptr()
+    if want_trajectory:
+        res.trajectory = buf("trajectory", (H, B, no))
+        cfg.trajectory = res.trajectory.data_ptr()
+    if stats_pivot is not None:
+        stats_pivot = _lib.f64(stats_pivot, (no,)).contiguous()
+        nb = _lib.lib().swm_rollout_stats_blocks(ctypes.byref(params), ctypes.byref(cfg))
+        res.stats_partial = buf("stats_partial", (nb, 2, no))
+        res.stats_blocks = nb
+        res.samples = float(B) * float(H)
+        cfg.stats_partial, cfg.stats_pivot = res.stats_partial.data_ptr(), stats_pivot.data_ptr()
+        keep.append(stats_pivot)
+    if screen is not None:
+        cfg.screen.enabled = 1
+        cfg.screen.sim = screen["sim_params"]
+        cfg.screen.sim_thresh = float(screen["sim_thresh"])
+        cfg.screen.real_thresh = float(screen["real_thresh"])
+        res.violations = buf("violations", (B,), torch.int32)
+        res.frozen_at = buf("frozen_at", (B,), torch.int32)
+        cfg.screen.violations = res.violations.data_ptr()
+        cfg.screen.frozen_at = res.frozen_at.data_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().swm_rollout(ctypes.byref(params), ctypes.byref(cfg), _lib.stream_ptr()))
+    return res
+
+
+def _philox(seed, iteration, dir0, dist):
+    p = _lib.SwmPhilox()
+    p.seed, p.iteration, p.dir0, p.dist = int(seed) & (2 ** 64 - 1), int(iteration), int(dir0), int(dist)
+    return p
+
+
+def philox_deltas(seed, iteration, dir0, count, wsize, dist=DELTA_PM1, device="cuda"):
+    """delta_k for k = dir0..dir0+count-1 as [count, wsize] -- what the kernels regenerate."""
+    _lib.require_cuda()
+    out = torch.empty(count, wsize, dtype=torch.float64, device=device)
+    ph = _philox(seed, iteration, dir0, dist)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().swm_philox_deltas(ctypes.byref(ph), count, wsize, _lib.ptr(out),
+                                                _lib.stream_ptr()))
+    return out
+
+
+def ars_topb(returns, mask=None, out=None):
+    """returns[2N] -> order[N] int32 (sort_directions; ties: higher index first, NaN first)."""
+    _lib.require_cuda()
+    returns = _lib.f64(returns).contiguous()
+    N = returns.numel() // 2
+    order = torch.empty(N, dtype=torch.int32, device=returns.device) if out is None else out
+    with torch.cuda.device(returns.device):
+        _lib.check(_lib.lib().swm_ars_topb(_lib.ptr(returns), _lib.ptr(mask), N, _lib.ptr(order),
+                                           _lib.stream_ptr()))
+    return order
+
+
+def update_args(semantics, N, b):
+    """(use_order, n_order, divisor, ddof) of the three reference update rules."""
+    if semantics == ARS_AGENT:   # ars/ars_agent.py:110-130: every sorted direction, divisor b
+        return True, N, float(b), 0
+    if semantics == ARS_TOPB:    # safe_ars/ars.py:96 + :48-65: order[:b], divisor len(order)
+        return True, min(b, N), 0.0, 0
+    if semantics == ARS_RLGLUE:  # rlglue/agent/SwimmerAgent.py:223-241: first b, sample std
+        return False, min(b, N), float(b), 1
+    raise ValueError("unknown ARS semantics %r" % (semantics,))
+
+
+def ars_update(W, returns, N, *, order=None, n_order=None, divisor=0.0, ddof=0, alpha=1.0, seed=0,
+               iteration=0, dir0=0, delta_dist=DELTA_PM1, deltas=None, mask=None, sigma_out=None):
+    """In-place W += alpha * sum_{k in order[:n_order]} (r+ - r-) delta_k / (divisor * sigma_R)."""
+    _lib.require_cuda()
+    assert W.is_contiguous() and W.dtype == torch.float64
+    ph = _philox(seed, iteration, dir0, delta_dist)
+    if deltas is not None:
+        deltas = _lib.f64(deltas).contiguous().reshape(N, W.numel())
+    n_order = N if n_order is None else int(n_order)
+    with torch.cuda.device(W.device):
+        _lib.check(_lib.lib().swm_ars_update(_lib.ptr(W), W.numel(), _lib.ptr(returns), N,
+                                             _lib.ptr(order), n_order, _lib.ptr(mask),
+                                             float(divisor), int(ddof), float(alpha),
+                                             ctypes.byref(ph), _lib.ptr(deltas), _lib.ptr(sigma_out),
+                                             _lib.stream_ptr()))
+    return W
+
+
+def screen_mask(sim_returns, threshold, mask_out=None, n_pass_out=None):
+    """mask[k] = r_sim+_k > threshold and r_sim-_k > threshold (ars_agent.py:150-157)."""
+    N = sim_returns.numel() // 2
+    dev = sim_returns.device
+    mask = torch.empty(N, dtype=torch.int32, device=dev) if mask_out is None else mask_out
+    n_pass = torch.empty(1, dtype=torch.int32, device=dev) if n_pass_out is None else n_pass_out
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().swm_screen_mask(_lib.ptr(sim_returns), N, float(threshold),
+                                              _lib.ptr(mask), _lib.ptr(n_pass), _lib.stream_ptr()))
+    return mask, n_pass
+
+
+def policy_actions(params, obs, policies, rollouts_per_policy=1, mean=None, inv_sigma=None,
+                   clip=False):
+    """Batched select_action (ars/environment.py:19-35): -> actions[B, n-1]."""
+    _lib.require_cuda()
+    n = params.n
+    B = obs.shape[0]
+    obs = _lib.f64(obs, (B, obs_dim(n))).contiguous()
+    policies = _lib.f64(policies).contiguous().reshape(-1, policy_size(n))
+    assert policies.shape[0] * rollouts_per_policy == B
+    out = torch.empty(B, act_dim(n), dtype=torch.float64, device=obs.device)
+    with torch.cuda.device(obs.device):
+        _lib.check(_lib.lib().swm_policy_actions(ctypes.byref(params), _lib.ptr(obs),
+                                                 _lib.ptr(policies), rollouts_per_policy,
+                                                 _lib.ptr(mean), _lib.ptr(inv_sigma), int(clip),
+                                                 _lib.ptr(out), B, _lib.stream_ptr()))
+    return out
+
+
+def stats_finalize(partial, samples, pivot, out=None, units=None):
+    """Per-block moment sums [nb, 2, F] -> record [1 + 2F] = (count, mean, M2).
+    count = samples (* units[0] if the device int32 `units` is given)."""
+    nb, _, F = partial.shape
+    rec = torch.empty(1 + 2 * F, dtype=torch.float64, device=partial.device) if out is None else out
+    with torch.cuda.device(partial.device):
+        _lib.check(_lib.lib().swm_stats_finalize(_lib.ptr(partial), nb, F, float(samples),
+                                                 _lib.ptr(units), _lib.ptr(pivot), _lib.ptr(rec),
+                                                 _lib.stream_ptr()))
+    return rec
+
+
+def stats_merge(running, records, mean_out=None, inv_sigma_out=None):
+    """running <- merge(running, records[0], ..) in index order; optional mean / inv_sigma."""
+    F = (running.numel() - 1) // 2
+    records = records.reshape(-1, 1 + 2 * F)
+    with torch.cuda.device(running.device):
+        _lib.check(_lib.lib().swm_stats_merge(_lib.ptr(running), _lib.ptr(records), records.shape[0],
+                                              F, _lib.ptr(mean_out), _lib.ptr(inv_sigma_out),
+                                              _lib.stream_ptr()))
+    return running
+
+
+def reduce_returns(returns, R, out=None):
+    G = returns.numel() // R
+    o = torch.empty(G, dtype=torch.float64, device=returns.device) if out is None else out
+    with torch.cuda.device(returns.device):
+        _lib.check(_lib.lib().swm_reduce_returns(_lib.ptr(returns), G, R, _lib.ptr(o),
+                                                 _lib.stream_ptr()))
+    return o
+
+
+def fp64_probe(blocks, threads, iters, sink):
+    flops = ctypes.c_double(0.0)
+    with torch.cuda.device(sink.device):
+        _lib.check(_lib.lib().swm_fp64_probe(blocks, threads, iters, _lib.ptr(sink),
+                                             ctypes.byref(flops), _lib.stream_ptr()))
+    return flops.value

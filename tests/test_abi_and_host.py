@@ -1,0 +1,145 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/*.h declares, the
+binding's struct layouts match the build, and the host-side logic (config dataclasses, database
+format, sharding, update-rule table) behaves like the reference's."""
+import ctypes
+import os
+import re
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = []
+    for h in ("swimmer_ars.h", "swimmer_rlglue_env.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        names += re.findall(r"^SWM_API[^;(]*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", src, flags=re.M)
+    src = open(os.path.join(ROOT, "include", "rlglue_types.h")).read()
+    names += re.findall(r"\bvoid\s+(allocateRLStruct|clearRLStruct)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol(S):
+    L = ctypes.CDLL(S._lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 25 and "swm_rollout" in names and "env_step" in names
+    for name in names:
+        assert hasattr(L, name), "missing export: " + name
+
+
+def test_struct_layouts_match_build(S):
+    L = S._lib.lib()
+    v = [ctypes.c_int() for _ in range(4)]
+    assert L.swm_abi_struct_sizes(*[ctypes.byref(x) for x in v]) == 0
+    assert [x.value for x in v] == [ctypes.sizeof(S._lib.SwmParams), ctypes.sizeof(S._lib.SwmPhilox),
+                                    ctypes.sizeof(S._lib.SwmScreen), ctypes.sizeof(S._lib.SwmRollout)]
+    assert L.swm_abi_version() == 1
+    assert L.swm_strerror(-2) == b"unsupported configuration"
+
+
+def test_no_cpu_fallback(S):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    p = S.make_params(n=3)
+    with pytest.raises(S.SwimmerLibError):
+        S.ops.step_batched(p, torch.zeros(1, 8, dtype=torch.float64), torch.zeros(1, 2, dtype=torch.float64))
+    with pytest.raises(S.SwimmerLibError):
+        env = S.SwimmerEnv(n=3)
+        env.reset()
+        env.step([0., 0.])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "safe-exploration-with-simulator-in-rl-algorithms_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower(), (dirpath, f)
+
+
+def test_parameters_and_threshold(S):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "misc.npz"))
+    for K, A, B, H, want in g["threshold_alpha"]:
+        assert abs(S.Threshold(K=K, A=A, B=B).compute_alpha(int(H)) - want) <= 1e-12 * abs(want)
+    ep = S.EnvParam("x", n=3, H=10, l_i=1., m_i=1., h=1e-3, k=10., epsilon=0.)
+    ap = S.ARSParam("a", V1=True, n_iter=1, H=10, N=2, b=1, alpha=.1, nu=.1, safe=False, threshold=0, initial_w="Zero")
+    assert (ep.n, ap.N, ap.initial_w) == (3, 2, "Zero")
+    assert [f for f in ep.__dataclass_fields__] == ["name", "n", "H", "l_i", "m_i", "h", "k", "epsilon"]
+
+
+def test_database_roundtrip(S):
+    db = S.Database()
+    for i in range(3):
+        db.add_trajectory(np.full((5, 8), float(i)), np.full((2, 8), -float(i)))
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "d.npz")
+        db.save(path)
+        z = np.load(path)
+        assert set(z.files) == {"policies", "trajectories"} and z["trajectories"].shape == (3, 5, 8)
+        db2 = S.Database(); db2.load(path)
+        assert db2.size == 3 and np.all(db2.policies[2] == -2.0)
+
+
+def test_update_rule_table(S):
+    assert S.ops.update_args(S.ARS_AGENT, 8, 3) == (True, 8, 3.0, 0)    # all N used, divisor b
+    assert S.ops.update_args(S.ARS_TOPB, 8, 3) == (True, 3, 0.0, 0)     # order[:b], divisor len(order)
+    assert S.ops.update_args(S.ARS_RLGLUE, 8, 3) == (False, 3, 3.0, 1)  # first b, sample std
+
+
+def test_swimmer_env_host_surface(S):
+    env = S.SwimmerEnv(n=5)
+    assert env.observation_space.shape == (12,) and env.action_space.shape == (4,)
+    assert env.reset() == [0., 0.] + [np.pi / 2, 0.] * 5
+    env.set_state(list(range(12)))
+    assert env.get_state() == [float(i) for i in range(12)]
+    assert env.get_reward() == 0.0 and env.check_terminal() is False
+    e2 = S.make()
+    assert e2.n == 5 and e2.envName == "LeonSwimmer-v0"
+    r = S.SwimmerEnv(n=3, variant="rlglue")
+    assert r.reset() == [0.001] * 8
+
+
+def _dist_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    sys.path.insert(0, ROOT)
+    import swimmer_ars_b200 as S
+    from swimmer_ars_b200 import distributed as D
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, F = 8, 4
+    lo, hi = D.shard_directions(N, rank, world)
+    local = torch.arange(2 * lo, 2 * hi, dtype=torch.float64)          # returns of my directions
+    rec = torch.cat([torch.tensor([float(rank + 1)]), torch.full((F,), float(rank)), torch.full((F,), 10. * rank)])
+    packed = D.pack_record(local, rec)
+    out = torch.zeros(world * packed.numel(), dtype=torch.float64)
+    dist.all_gather_into_tensor(out, packed)
+    returns, records = D.unpack_records(out, world, 2 * (hi - lo), F)
+    q.put((rank, returns.tolist(), records.tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharding_and_packed_allgather_gloo(S):
+    """world_size 2 on CPU (gloo): the packed per-rank record round-trips through one all-gather
+    and every rank reconstructs the same 2N returns in direction order + the records in rank order."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + os.getpid() % 200
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    for rank, returns, records in got:
+        assert returns == [float(i) for i in range(16)]
+        assert records[0][0] == 1.0 and records[1][0] == 2.0 and records[1][1] == 1.0 and records[1][-1] == 10.0
+    from swimmer_ars_b200 import distributed as D
+    assert D.shard_directions(1024, 3, 8) == (384, 512)
+    with pytest.raises(ValueError):
+        D.shard_directions(10, 0, 4)

@@ -1,0 +1,248 @@
+"""ARS update / agent parity against the reference fixtures and the oracle.
+north_star: top-b selection bit-exact given identical rewards; weight updates within 1e-6."""
+import io
+import contextlib
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+def _cuda(a, dtype=np.float64):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=dtype)).cuda()
+
+
+def test_topb_bit_exact(S):
+    g = golden("topb.npz")
+    for N in (1, 2, 8, 33, 256, 1024):
+        order = S.ops.ars_topb(_cuda(g[f"returns_{N}"])).cpu().numpy()
+        np.testing.assert_array_equal(order, g[f"order_{N}"])
+    np.testing.assert_array_equal(S.ops.ars_topb(_cuda(g["returns_ties"])).cpu().numpy(), g["order_ties"])
+
+
+def test_topb_large_random_vs_numpy(S):
+    rng = np.random.default_rng(4)
+    for N in (4096, 5000):
+        r = rng.normal(size=2 * N)
+        want = np.argsort(np.maximum(r[0::2], r[1::2]), kind="stable")[::-1]
+        np.testing.assert_array_equal(S.ops.ars_topb(_cuda(r)).cpu().numpy(), want)
+    # all-equal keys: stable rule = higher index first
+    np.testing.assert_array_equal(S.ops.ars_topb(_cuda(np.zeros(64))).cpu().numpy(), np.arange(32)[::-1])
+    # screened-out directions sort last
+    r = rng.normal(size=16); mask = np.array([1, 0, 1, 1, 0, 1, 1, 1], dtype=np.int32)
+    order = S.ops.ars_topb(_cuda(r), _cuda(mask, np.int32)).cpu().numpy()
+    assert set(order[-2:]) == {1, 4} and sorted(order) == list(range(8))
+
+
+@pytest.mark.parametrize("semantics", [0, 1, 2])
+@pytest.mark.parametrize("n,N,b", [(3, 8, 8), (5, 64, 16), (10, 33, 7)])
+def test_update_matches_oracle(S, O, semantics, n, N, b):
+    ws = (n - 1) * (2 * n + 2)
+    rng = np.random.default_rng(n * N + semantics)
+    W0, rets = rng.normal(size=ws), rng.normal(size=2 * N) * 30
+    seed, it = 99, 7
+    dist = 1 if semantics == 2 else 0
+    deltas = np.stack([O.philox_delta(seed, it, k, ws, dist=dist) for k in range(N)])
+    want, want_sigma = O.update_policy(W0, deltas, rets, b=b, alpha=0.02, semantics=semantics)
+    use_order, n_order, divisor, ddof = S.ops.update_args(semantics, N, b)
+    for explicit in (False, True):
+        W = _cuda(W0)
+        r = _cuda(rets)
+        order = S.ops.ars_topb(r) if use_order else None
+        sig = torch.zeros(1, dtype=torch.float64, device="cuda")
+        S.ops.ars_update(W, r, N, order=order, n_order=n_order, divisor=divisor, ddof=ddof, alpha=0.02,
+                         seed=seed, iteration=it, delta_dist=dist,
+                         deltas=_cuda(deltas) if explicit else None, sigma_out=sig)
+        assert rel_err(W.cpu().numpy(), want) < 1e-12
+        assert abs(float(sig.cpu()[0]) - want_sigma) < 1e-12 * want_sigma
+
+
+def test_ars_agent_config1_matches_reference_run(S):
+    """BASELINE config 1 (n=3, V1, N=8, b=8, H=1000, seed 0): same numpy seed => the reference's own
+    iteration returns and policies (fixture recorded from the unmodified reference)."""
+    g = golden("ars_agent.npz")
+    ep = S.EnvParam("LeonSwimmer-RealWorld", n=3, H=1000, l_i=1., m_i=1., h=1e-3, k=10., epsilon=0)
+    ap = S.ARSParam("RLControl", V1=True, n_iter=2, H=1000, N=8, b=8, alpha=0.0075, nu=0.01,
+                    safe=False, threshold=0, initial_w="Zero")
+    ag = S.ARSAgent(ep, ap, seed=0)
+    for it in range(3):
+        rets = ag.runOneIteration()
+        assert isinstance(rets, list) and len(rets) == 16
+        np.testing.assert_allclose(rets, g["c1_returns"][it], rtol=TOL, atol=1e-9)
+        assert rel_err(ag.policy, g["c1_policies"][it]) < TOL
+    # the reference-shaped helper methods
+    d = 2 * g["c1_rand"][0] - 1
+    order = ag.sort_directions(list(d), g["c1_returns"][0].tolist())
+    mx = np.maximum(g["c1_returns"][0][0::2], g["c1_returns"][0][1::2])
+    assert order == np.argsort(mx)[::-1].tolist()
+    ag.policy = np.zeros((2, 8))
+    ag.update_policy(list(d), g["c1_returns"][0].tolist(), order)
+    assert rel_err(ag.policy, g["c1_policies"][0]) < 1e-10
+
+
+def test_ars_agent_v2_matches_reference_run(S):
+    g = golden("ars_agent.npz")
+    ep = S.EnvParam("x", n=3, H=250, l_i=.8, m_i=1.2, h=1e-3, k=10.2, epsilon=0)
+    ap = S.ARSParam("x", V1=False, n_iter=2, H=250, N=4, b=4, alpha=0.0075, nu=0.01,
+                    safe=False, threshold=0, initial_w="Zero")
+    ag = S.ARSAgent(ep, ap, seed=3)
+    assert np.all(ag.mean == 0) and np.all(ag.covariance == np.eye(8))
+    for it in range(3):
+        rets = ag.runOneIteration()
+        np.testing.assert_allclose(rets, g["v2_returns"][it], rtol=TOL, atol=1e-9)
+        assert rel_err(ag.policy, g["v2_policies"][it]) < TOL
+        np.testing.assert_allclose(ag.mean, g["v2_means"][it], rtol=TOL, atol=1e-9)
+        np.testing.assert_allclose(np.diag(ag.covariance), g["v2_vars"][it], rtol=TOL)
+
+
+def test_ars_agent_run_training_curve(S):
+    g = golden("ars_agent.npz")
+    ep = S.EnvParam("x", n=3, H=200, l_i=1., m_i=1., h=1e-3, k=10., epsilon=0)
+    ap = S.ARSParam("x", V1=True, n_iter=4, H=200, N=2, b=2, alpha=0.02, nu=0.05,
+                    safe=False, threshold=0, initial_w="Zero")
+    with tempfile.TemporaryDirectory() as td:
+        ag = S.ARSAgent(ep, ap, seed=11)
+        curve = ag.runTraining(save_data_path=os.path.join(td, "db.npz"),
+                               save_policy_path=os.path.join(td, "pol"))
+        assert isinstance(curve, np.ndarray) and curve.shape == (5,)
+        np.testing.assert_allclose(curve, g["rt_curve"], rtol=TOL, atol=1e-9)
+        assert rel_err(ag.policy, g["rt_policy"]) < TOL
+        assert rel_err(np.load(os.path.join(td, "pol.npy")), g["rt_policy"]) < TOL
+        assert ag.database.size == 5 * 4 and len(ag.database.trajectories[0]) == 200
+
+
+def test_ars_agent_safe_mode_matches_reference_run(S):
+    """Reward-constraint safe exploration, N=1 (the reference's own use): screened iterations do no
+    real rollout and no update; surviving ones reproduce the reference's returns and policies."""
+    g = golden("ars_agent_safe.npz")
+    l, m, k = g["sim_params"]
+    with tempfile.TemporaryDirectory() as td:
+        wpath = os.path.join(td, "w0.npy"); np.save(wpath, g["W0"])
+        dpath = os.path.join(td, "db.npz")
+        np.savez(dpath, policies=[g["W0"]], trajectories=[np.zeros((50, 8))])
+        ep = S.EnvParam("real", n=3, H=300, l_i=.8, m_i=1.2, h=1e-3, k=10.2, epsilon=0.001)
+        ap = S.ARSParam("x", V1=True, n_iter=7, H=300, N=1, b=1, alpha=0.0075, nu=0.01, safe=True,
+                        threshold=float(g["threshold"]), initial_w=wpath)
+        np.random.seed(99)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ag = S.ARSAgent(ep, ap, data_path=dpath, seed=4, approx_error=0.001,
+                            sim_thresh=S.Threshold(K=1, A=0.1, B=0.001))
+        assert abs(ag.sim_threshold - float(g["sim_threshold"])) < 1e-12
+        np.testing.assert_allclose([ag.estimated_param.l_i, ag.estimated_param.m_i, ag.estimated_param.k],
+                                   [l, m, k], rtol=1e-14)
+        assert (ep.l_i, ep.m_i, ep.k) == (.8, 1.2, 10.2)  # caller's dataclass is not mutated (D-5)
+        for it in range(8):
+            with contextlib.redirect_stdout(io.StringIO()):
+                rets = ag.runOneIteration()
+            want = g["returns"][it]
+            if np.isnan(want[0]):
+                assert rets == []
+            else:
+                np.testing.assert_allclose(rets, want, rtol=TOL)
+            assert rel_err(ag.policy, g["policies"][it]) < TOL
+
+
+def test_basic_and_safe_ars_train_match_reference_run(S):
+    g = golden("safe_ars.npz")
+    real = S.SwimmerEnv("RealWorld", n=3)
+    ag = S.Basic_ARS()
+    np.random.seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        curve, states = ag.train(3, real, 4, 2, 0.02, 0.05, 200)
+    np.testing.assert_allclose(curve, g["basic_curve"], rtol=TOL, atol=1e-10)
+    assert rel_err(ag.policy, g["basic_policy"]) < TOL
+    assert states.shape == (3 * 8, 200, 8)
+    assert rel_err(states[-1][-1], g["basic_states_last"]) < 1e-8
+    m, l, k = g["sim_mlk"]
+    sim = S.SwimmerEnv("Simulator", n=3, m_i=m, l_i=l, k=k)
+    sag = S.Safe_ARS(S.builtin_cost, 3.0, 2.0, sim)
+    np.random.seed(2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        curve, _ = sag.train(2, real, 3, 2, 0.02, 0.3, 150)
+    np.testing.assert_allclose(curve, g["safetrain_curve"], rtol=TOL, atol=1e-10)
+    assert rel_err(sag.policy, g["safetrain_policy"]) < TOL
+
+
+def test_philox_agent_matches_oracle_loop(S, O):
+    """delta_source='philox' (nothing uploaded): an oracle loop fed the same Philox deltas gives the
+    same returns, policy and V2 statistics after 3 iterations (n=5, V2, true top-b)."""
+    n, N, b, H, nu, alpha, seed = 5, 6, 3, 120, 0.03, 0.02, 1234
+    ps, po = S.make_params(n=n), O.make_params(n=n)
+    ws = (n - 1) * (2 * n + 2)
+    eng = S.ArsEngine(ps, N=N, b=b, alpha=alpha, nu=nu, H=H, v2=True, semantics=S.ARS_TOPB, seed=seed,
+                      distributed=False)
+    W = np.zeros(ws); mean, inv_sigma = np.zeros(2 * n + 2), np.ones(2 * n + 2); states = []
+    for it in range(3):
+        got = eng.run_iteration().cpu().numpy()
+        deltas = np.stack([O.philox_delta(seed, it, k, ws) for k in range(N)])
+        rets = []
+        for kdir in range(N):
+            for sign in (+1, -1):
+                r, _, traj = O.rollout(po, 0, H, policy=W + sign * nu * deltas[kdir], mean=mean,
+                                       inv_sigma=inv_sigma, want_traj=True)
+                rets.append(r); states.append(traj)
+        np.testing.assert_allclose(got, rets, rtol=TOL, atol=1e-9)
+        W, _ = O.update_policy(W, deltas, np.array(rets), b=b, alpha=alpha, semantics=1)
+        mean, var = O.mean_var(np.concatenate(states)); inv_sigma = var ** -0.5
+        assert rel_err(eng.W.cpu().numpy(), W) < TOL
+        np.testing.assert_allclose(eng.mean.cpu().numpy(), mean, rtol=TOL, atol=1e-9)
+        np.testing.assert_allclose(eng.inv_sigma.cpu().numpy(), inv_sigma, rtol=TOL)
+
+
+def test_engine_masked_update_and_resume(S, O):
+    """Reward-constraint screening with N > 1 (the case the reference cannot run, SURVEY D-2):
+    survivors are compacted; the update equals the oracle's over the surviving triples.  Also
+    state_dict round trip => bit-identical continuation."""
+    n, N, H, nu = 3, 8, 100, 0.05
+    real = S.make_params(n=n, l_i=.8, m_i=1.2, k=10.2)
+    sim = S.make_params(n=n, l_i=.81, m_i=1.21, k=10.25)
+    W0 = np.random.default_rng(0).uniform(-1, 1, 16) * 0.3
+    probe = S.ArsEngine(sim, N=N, b=N, alpha=0.01, nu=nu, H=H, seed=5, initial_policy=W0, distributed=False)
+    sim_ret = probe.run_iteration(update=False).cpu().numpy()
+    thr = float(np.median(np.minimum(sim_ret[0::2], sim_ret[1::2])))
+    eng = S.ArsEngine(real, N=N, b=N, alpha=0.01, nu=nu, H=H, seed=5, initial_policy=W0,
+                      sim_params=sim, sim_threshold=thr, distributed=False)
+    rets = eng.run_iteration().cpu().numpy()
+    ok = (sim_ret[0::2] > thr) & (sim_ret[1::2] > thr)
+    assert 0 < ok.sum() < N
+    assert np.array_equal(np.isnan(rets[0::2]), ~ok) and np.array_equal(eng.mask.cpu().numpy() != 0, ok)
+    deltas = np.stack([O.philox_delta(5, 0, k, 16) for k in range(N)])
+    keep = np.nonzero(ok)[0]
+    r_keep = rets.reshape(N, 2)[keep].ravel()
+    want, _ = O.update_policy(W0, deltas[keep], r_keep, b=N, alpha=0.01, semantics=0)
+    assert rel_err(eng.W.cpu().numpy(), want) < 1e-12
+    sd = eng.state_dict()
+    a = eng.run_iteration().clone()
+    eng2 = S.ArsEngine(real, N=N, b=N, alpha=0.01, nu=nu, H=H, seed=0, sim_params=sim, sim_threshold=thr,
+                       distributed=False)
+    eng2.load_state_dict(sd)
+    b = eng2.run_iteration()
+    assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)) and torch.equal(eng.W, eng2.W)
+
+
+def test_estimator_objective(S, O):
+    """Estimator.I (ars/estimator.py:36-62): zero at the true parameters (the reference's own
+    self-check, estimator.py:136), and equal to the oracle's value elsewhere."""
+    n, H = 3, 80
+    po = O.make_params(n=n, l_i=1., m_i=1., k=10.)
+    rng = np.random.default_rng(8)
+    W = rng.uniform(-1, 1, (2, 8)) * 0.5
+    _, _, traj = O.rollout(po, 0, H, policy=W, want_traj=True)
+    db = S.Database(); db.add_trajectory(traj.tolist(), W)
+    guess = S.EnvParam("sim", n=n, H=H, m_i=1.01, l_i=1.01, h=0.001, k=10.01, epsilon=0.01)
+    est = S.Estimator(db, guess, capacity=1)
+    assert est.I([1.0, 1.0, 10.0]) < 1e-12
+    x = [1.05, 0.97, 10.4]
+    p2 = O.make_params(n=n, m_i=x[0], l_i=x[1], k=x[2])
+    want = 0.0
+    for t in range(H - 1):
+        nxt, _ = O.step(p2, 0, traj[t], W @ traj[t])
+        want += np.linalg.norm(nxt - traj[t + 1])
+    assert abs(est.I(x) - want) < 1e-9 * want

@@ -1,0 +1,125 @@
+"""CUDA single-step parity (through the C ABI) against the oracle and the golden fixtures.
+Tolerance from BASELINE.json north_star: single-step states within 1e-12 relative (norm-wise,
+absolute floor 1: Gdot after one step from reset is pure round-off)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden, rand_states, rel_err
+
+pytestmark = pytest.mark.gpu
+STEP_TOL = 1e-12
+
+
+def _cuda(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+@pytest.mark.parametrize("n", list(range(2, 11)))
+@pytest.mark.parametrize("variant", [0, 1])
+def test_step_matches_oracle_random(S, O, n, variant):
+    rng = np.random.default_rng(100 * n + variant)
+    B = 257  # ragged: not a multiple of the block size
+    l, m, k, h = rng.uniform(.5, 1.5), rng.uniform(.5, 1.5), rng.uniform(5, 15), 0.003
+    po = O.make_params(n=n, l_i=l, m_i=m, k=k, h=h, direction=(0.6, -0.8))
+    ps = S.make_params(n=n, l_i=l, m_i=m, k=k, h=h, direction=(0.6, -0.8))
+    st, ac = rand_states(rng, n, B), rng.uniform(-5, 5, (B, n - 1))
+    want, want_r = O.step_batch(po, variant, st, ac)
+    got, got_r = S.ops.step_batched(ps, _cuda(st), _cuda(ac), variant)
+    assert rel_err(got.cpu().numpy(), want) < STEP_TOL
+    assert rel_err(got_r.cpu().numpy(), want_r) < STEP_TOL
+    acc = S.ops.accelerations_batched(ps, _cuda(st), _cuda(ac), variant).cpu().numpy()
+    for i in range(0, B, 37):
+        gdd, thdd = O.accelerations(po, variant, st[i], ac[i])
+        # accelerations are O(1e1..1e3); allow conditioning of the solve (cond <= ~230 gym)
+        assert rel_err(acc[i], np.concatenate([gdd, thdd])) < (1e-11 if variant == 0 else 1e-9)
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 10])
+def test_gym_step_matches_reference_fixture(S, n):
+    g = golden("gym_step.npz")
+    for t in range(len(g[f"n{n}_state"])):
+        l, m, k, h = g[f"n{n}_params"][t]
+        p = S.make_params(n=n, l_i=l, m_i=m, k=k, h=h, direction=(1., 0.) if t % 2 == 0 else (0.6, -0.8))
+        got, r = S.ops.step_batched(p, _cuda(g[f"n{n}_state"][t:t + 1]), _cuda(g[f"n{n}_action"][t:t + 1]))
+        assert rel_err(got.cpu().numpy()[0], g[f"n{n}_next"][t]) < STEP_TOL
+        assert abs(float(r.cpu()[0]) - g[f"n{n}_reward"][t]) < STEP_TOL * max(1, abs(g[f"n{n}_reward"][t]))
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 10])
+def test_rlglue_step_matches_reference_fixture(S, n):
+    g = golden("rlglue_step.npz")
+    for t in range(len(g[f"n{n}_state"])):
+        l, m, k, h = g[f"n{n}_params"][t]
+        p = S.make_params(n=n, l_i=l, m_i=m, k=k, h=h)
+        got, _ = S.ops.step_batched(p, _cuda(g[f"n{n}_state"][t:t + 1]), _cuda(g[f"n{n}_action"][t:t + 1]), 1)
+        assert rel_err(got.cpu().numpy()[0], g[f"n{n}_next"][t]) < 1e-11
+
+
+def test_rlglue_golden_text(S):
+    gold = json.load(open(os.path.join(GOLDEN, "rlglue_golden.json")))
+    p = S.make_params(n=3, h=gold["params"]["h_inferred"])
+    st, tq = _cuda([gold["state"]]), _cuda([gold["torque"]])
+    acc = S.ops.accelerations_batched(p, st, tq, 1).cpu().numpy()[0]
+    np.testing.assert_allclose(acc[:2], gold["G_dotdot_6digits"], rtol=5e-6)
+    np.testing.assert_allclose(acc[2:], gold["theta_dotdot_6digits"], rtol=5e-6)
+    nxt, _ = S.ops.step_batched(p, st, tq, 1)
+    np.testing.assert_allclose(nxt.cpu().numpy()[0], gold["state_after_update_6digits"], rtol=5e-6)
+
+
+def test_swimmer_env_gym_surface(S, O):
+    """reset/step/set_state/get_state keep the reference's conventions (lists, 4-tuple, no clip)."""
+    env = S.SwimmerEnv(n=3)
+    ob = env.reset()
+    assert isinstance(ob, list) and len(ob) == 8 and ob[2] == np.pi / 2
+    assert env.observation_space.shape[0] == 8 and env.action_space.shape[0] == 2
+    ob, r, done, info = env.step(np.array([2.5, 2.5]))
+    want = [-8.32667268468868e-19, -4.622231866529367e-35, 1.5707963267948966, -0.015000000000000006,
+            1.5707963267948966, 3.4416913763379856e-18, 1.5707963267948966, 0.014999999999999996]
+    assert isinstance(ob, list) and done is False and info == {}
+    assert rel_err(ob, want) < STEP_TOL
+    # no clipping on the gym path: an out-of-range torque is used as is
+    p = O.make_params(n=3)
+    st = rand_states(np.random.default_rng(0), 3, 1)[0]
+    env.set_state(st.tolist())
+    ob, r, _, _ = env.step([50., -80.])
+    w, wr = O.step(p, 0, st, [50., -80.])
+    assert rel_err(ob, w) < STEP_TOL and abs(r - wr) < STEP_TOL * max(1, abs(wr))
+    with pytest.raises(AssertionError):
+        env.set_state([0.] * 7)
+    gdd, thdd = env.compute_accelerations([1., -1.], st[:2], st[2::2], st[3::2])
+    og, ot = O.accelerations(p, 0, st, [1., -1.])
+    assert rel_err(np.concatenate([gdd, thdd]), np.concatenate([og, ot])) < 1e-11
+
+
+def test_step_batched_env_api(S, O):
+    env = S.SwimmerEnv(n=5, l_i=.9, k=11.)
+    p = O.make_params(n=5, l_i=.9, k=11.)
+    rng = np.random.default_rng(3)
+    st = rand_states(rng, 5, 64)
+    env.set_state_batched(st)
+    cur = st.copy()
+    for t in range(5):
+        ac = rng.uniform(-5, 5, (64, 4))
+        states, rew, dones, _ = env.step_batched(ac)
+        cur, wr = O.step_batch(p, 0, cur, ac)
+        assert rel_err(states.cpu().numpy(), cur) < STEP_TOL * (t + 1)
+        assert not bool(dones.any())
+    assert tuple(env.reset_batched(7).shape) == (7, 12)
+
+
+def test_empty_and_bad_arguments(S):
+    p = S.make_params(n=3)
+    z = torch.zeros(0, 8, dtype=torch.float64, device="cuda")
+    a = torch.zeros(0, 2, dtype=torch.float64, device="cuda")
+    out, r = S.ops.step_batched(p, z, a)
+    assert out.shape[0] == 0
+    with pytest.raises(ValueError):
+        S.make_params(n=11)
+    with pytest.raises(ValueError):
+        S.make_params(n=1)
+    with pytest.raises(ValueError):
+        S.ops.step_batched(p, torch.zeros(4, 8, device="cuda"), torch.zeros(4, 2, device="cuda"))  # fp32
