@@ -30,8 +30,8 @@ WORKLOAD = "config[1]: 3-segment swimmer, 65,536 envs per GPU, fixed random acti
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-ars", action="store_true", help="skip the supplementary ARS-iteration measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -161,8 +161,12 @@ class ClockSampler:
             for nm, v in zip(names, c[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        # idle samples (before the first launch) sit at the idle clock: take the median of the upper half
+        hot = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(hot)) if hot else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm),
+                "note": "nvidia-smi -lms 100 from before warm-up to the end of the e2e region, same kernel "
+                        "kept running until >=5 samples; median of the upper half of samples"}
 
 
 def run_b200(args):
@@ -206,10 +210,10 @@ def run_b200(args):
         best = max(best, flops / (e0.elapsed_time(e1) * 1e-3))
     fp64_peak_tflops = best / 1e12
 
+    sampler = ClockSampler(device.index) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         one_step()
     barrier()
-    sampler = ClockSampler(device.index) if rank == 0 else None
     # ---- device-resident timing: K steps, each its own event pair, L2 flushed in between ----
     evs = []
     t_wall0 = time.perf_counter()
@@ -247,6 +251,15 @@ def run_b200(args):
         evs2.append((e0, e1))
     barrier()
     t_e2e = torch.tensor([sum(a.elapsed_time(b) for a, b in evs2)], dtype=torch.float64, device=device)
+    # nvidia-smi needs ~100 ms per sample: if the timed regions above were too short to be sampled,
+    # keep the same kernel running (untimed) until a few samples under load exist.
+    if sampler:
+        t_end = time.perf_counter() + 3.0
+        n0 = len(sampler.rows)
+        while len(sampler.rows) < n0 + 5 and time.perf_counter() < t_end:
+            for _ in range(20):
+                one_step()
+            torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)

@@ -24,11 +24,12 @@ __device__ __forceinline__ bool asc_less(double a, int ia, double b, int ib) {
 }
 
 // order[rank_i] = i, rank_i = #directions that precede i in descending order.  Rank by counting:
-// O(N^2) comparisons spread over N threads; no data-dependent control flow, any N.
+// one warp per direction i, lanes stride over j, integer warp reduction -- O(N^2) comparisons spread
+// over 32 N threads, no data-dependent control flow, exact for any N.
 __global__ void __launch_bounds__(kArsBlock)
 ars_rank_kernel(const double* __restrict__ returns, const int* __restrict__ mask, int N,
                 int* __restrict__ order) {
-  extern __shared__ double keys[];  // N keys, then N validity flags packed as doubles' sign? no: ints
+  extern __shared__ double keys[];  // N keys followed by N validity flags (int)
   int* valid = reinterpret_cast<int*>(keys + N);
   for (int i = threadIdx.x; i < N; i += kArsBlock) {
     const double a = returns[2 * i], b = returns[2 * i + 1];
@@ -36,18 +37,20 @@ ars_rank_kernel(const double* __restrict__ returns, const int* __restrict__ mask
     valid[i] = mask ? (mask[i] != 0) : 1;
   }
   __syncthreads();
-  const int i = blockIdx.x * kArsBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (kArsBlock / 32) + (threadIdx.x >> 5);
   if (i >= N) return;
   const double ki = keys[i];
   const int vi = valid[i];
   int rank = 0;
-  for (int j = 0; j < N; ++j) {
+  for (int j = lane; j < N; j += 32) {
     // j precedes i iff (j valid, i not) or (same validity and i <asc j)
     const int vj = valid[j];
     const bool before = (vj != vi) ? (vj > vi) : asc_less(ki, i, keys[j], j);
     rank += (j != i && before) ? 1 : 0;
   }
-  order[rank] = i;
+  rank = __reduce_add_sync(0xffffffffu, rank);
+  if (lane == 0) order[rank] = i;
 }
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -261,7 +264,8 @@ extern "C" int swm_ars_topb(const double* returns, const int32_t* mask, int N, i
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(ars_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return SWM_ERR_CUDA;
-  ars_rank_kernel<<<(N + kArsBlock - 1) / kArsBlock, kArsBlock, smem, (cudaStream_t)stream>>>(
+  const int per_block = kArsBlock / 32;
+  ars_rank_kernel<<<(N + per_block - 1) / per_block, kArsBlock, smem, (cudaStream_t)stream>>>(
       returns, mask, N, order);
   return SWM_CHECK_LAUNCH();
 }

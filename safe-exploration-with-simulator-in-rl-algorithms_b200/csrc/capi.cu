@@ -64,9 +64,10 @@ Phys make_phys(const swm_params_t* p) {
 
 int step_common(const swm_params_t* params, int variant, bool acc_only, const double* state_in,
                 const double* action, double* out, double* reward, int64_t B, void* stream) {
-  if (!params_ok(params) || !state_in || !action || !out || B < 0) return SWM_ERR_BAD_ARG;
+  if (!params_ok(params) || B < 0) return SWM_ERR_BAD_ARG;
   if (variant != SWM_DYN_GYM && variant != SWM_DYN_RLGLUE) return SWM_ERR_BAD_ARG;
-  if (B == 0) return SWM_OK;
+  if (B == 0) return SWM_OK;  // empty batch: nothing to do, pointers may be NULL
+  if (!state_in || !action || !out) return SWM_ERR_BAD_ARG;
   const Phys P = make_phys(params);
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(K) launch_step_n<K>(P, variant, acc_only, state_in, action, out, reward, (long long)B, st)
@@ -124,9 +125,10 @@ extern "C" int64_t swm_rollout_stats_blocks(const swm_params_t* params, const sw
 
 extern "C" int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg, void* stream) {
   if (!params_ok(params) || !cfg) return SWM_ERR_BAD_ARG;
-  if (cfg->B < 0 || cfg->H < 0 || cfg->rollouts_per_policy < 1 || !cfg->returns) return SWM_ERR_BAD_ARG;
+  if (cfg->B < 0 || cfg->H < 0 || cfg->rollouts_per_policy < 1) return SWM_ERR_BAD_ARG;
   if (cfg->variant != SWM_DYN_GYM && cfg->variant != SWM_DYN_RLGLUE) return SWM_ERR_BAD_ARG;
   if (cfg->B == 0) return SWM_OK;
+  if (!cfg->returns) return SWM_ERR_BAD_ARG;
   if (cfg->B > (int64_t)kRolloutBlock * 0x7fffffffLL) return SWM_ERR_BAD_ARG;
   RolloutArgs a;
   memset(&a, 0, sizeof(a));

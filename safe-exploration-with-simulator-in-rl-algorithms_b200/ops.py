@@ -54,6 +54,8 @@ def step_batched(params, states, actions, variant=GYM, out=None, want_reward=Tru
     states, actions = states.contiguous(), actions.contiguous()
     out = torch.empty_like(states) if out is None else out
     rew = torch.empty(B, dtype=torch.float64, device=states.device) if want_reward else None
+    if B == 0:
+        return out, rew
     with torch.cuda.device(states.device):
         _lib.check(_lib.lib().swm_step_batched(ctypes.byref(params), variant, _lib.ptr(states),
                                                _lib.ptr(actions), _lib.ptr(out), _lib.ptr(rew), B,
