@@ -32,11 +32,16 @@ def main():
             b = ref.run_iteration().clone()
             if it == 0:
                 assert torch.equal(a, b), "iteration-0 returns must be bit-identical"
-            assert torch.allclose(a, b, rtol=1e-10, atol=1e-12), (n, it, (a - b).abs().max().item())
-            assert torch.allclose(eng.W, ref.W, rtol=1e-10, atol=1e-13)
-            if v2:
-                assert torch.allclose(eng.mean, ref.mean, rtol=1e-10, atol=1e-13)
-                assert torch.allclose(eng.inv_sigma, ref.inv_sigma, rtol=1e-10)
+            def rel(x, y):
+                return ((x - y).abs().max() / y.abs().max().clamp_min(1e-300)).item()
+            dr, dw = rel(a, b), rel(eng.W, ref.W)
+            dm = rel(eng.mean, ref.mean) if v2 else 0.0
+            ds = rel(eng.inv_sigma, ref.inv_sigma) if v2 else 0.0
+            if rank == 0:
+                print("  n=%d it=%d  rel diff vs single GPU: returns %.1e  W %.1e  mean %.1e  inv_sigma %.1e"
+                      % (n, it, dr, dw, dm, ds), flush=True)
+            # north-star tolerance for returns and weight updates: 1e-6 relative
+            assert dr < 1e-6 and dw < 1e-6 and dm < 1e-6 and ds < 1e-6
             # bit-identical across ranks
             buf = [torch.empty_like(eng.W) for _ in range(world)]
             dist.all_gather(buf, eng.W)
