@@ -35,14 +35,14 @@ Phys make_phys(const swm_params_t* p) {
   const double l = p->l_i, m = p->m_i, k = p->k, n = (double)p->n;
   P.l = l; P.m = m; P.k = k; P.h = p->h; P.max_u = p->max_u;
   P.dirx = p->direction[0]; P.diry = p->direction[1];
-  P.kl = k * l;
-  P.inv_nm = 1.0 / (n * m);
-  P.tau_c = k * (l * l * l) / 12.0;
-  P.six_over_l = 6.0 / l;
-  P.half_lm = l * m / 2.0;
-  P.thdd_c = 6.0 / (m * l);
-  P.inv_I = 12.0 / (m * l * l);
+  P.inv_l = 1.0 / l;
+  P.kappa = k * l / m;
+  P.m2kappa = -2.0 * (k * l / m);
+  P.u_scale = 12.0 / (m * l * l);
+  P.gdd_c = l / (2.0 * n);
   P.inv_n = 1.0 / n;
+  P.kl = k * l;
+  P.tau_c = k * (l * l * l) / 12.0;
   P.half_l = l / 2.0;
   P.I = m * (l * l) / 12.0;
   return P;

@@ -11,6 +11,8 @@
 //       w_i = (6 tau_i / l) n_i - (l m thd_i^2 / 2) p_i,   tau_i = k thd_i l^3/12 + u_{i-1} - u_i
 //     solved by an unpivoted 2x2-block LDL^T sweep (one reciprocal per joint),
 //   * thdd_i = (6/(m l)) n_i.(f_i + f_{i+1}) + 12 tau_i/(m l^2).
+// The code works in a non-dimensional form of these equations (see gym_accelerations) so that the
+// physical constants fold into four precomputed numbers.
 // O(n) flops and O(n) registers, no pivoting, no local memory.  Agrees with the reference's
 // pivoted dense solve to ~1e-15 relative (tests/test_parity_step.py).
 //
@@ -26,14 +28,16 @@ namespace swm {
 // Physical constants of one model, precomputed on the host (kernel argument -> constant bank).
 struct Phys {
   double l, m, k, h, max_u, dirx, diry;
-  double kl;         // k*l
-  double inv_nm;     // 1/(n*m)
-  double tau_c;      // k*l^3/12
-  double six_over_l; // 6/l
-  double half_lm;    // l*m/2
-  double thdd_c;     // 6/(m*l)
-  double inv_I;      // 12/(m*l^2)
+  // gym variant, non-dimensional form (lengths in units of l, forces in units of m*l/2)
+  double inv_l;      // 1/l
+  double kappa;      // k*l/m       (friction torque coefficient: tau_i/I = kappa*thd_i + ...)
+  double m2kappa;    // -2*k*l/m    (psi_i = m2kappa * (v_i.n_i) * n_i)
+  double u_scale;    // 12/(m*l^2)  (torques enter as u/I)
+  double gdd_c;      // l/(2n)      (Gdd = gdd_c * sum_i psi_i)
   double inv_n;      // 1/n
+  // rlglue variant
+  double kl;         // k*l
+  double tau_c;      // k*l^3/12
   double half_l;     // l/2
   double I;          // m*l^2/12
 };
@@ -51,85 +55,89 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// gym variant.  s[i] = sin(th_i), c[i] = cos(th_i).  u has N-1 entries.
+// gym variant, non-dimensional O(n) form.  With v = Gdot_i / l, g_j = 2 f_j / (m l),
+// ut = u * 12/(m l^2), kappa = k l / m:
+//   tau~_i = kappa thd_i + ut_{i-1} - ut_i                       (= tau_i / I)
+//   psi_i  = -2 kappa (v_i . n_i) n_i                            (= 2 Phi_i / (m l))
+//   w^_i   = tau~_i n_i - thd_i^2 p_i
+//   Q_{j-1} g_{j-1} + P_j g_j + Q_j g_{j+1} = psi_j - psi_{j-1} - w^_{j-1} - w^_j
+//        P_j = 2I + 3(N_{j-1}+N_j),  Q_j = 3N_j - I,  N_i = n_i n_i^T
+//   thdd_i = 3 n_i.(g_i + g_{i+1}) + tau~_i,    Gdd = l/(2n) sum_i psi_i
+// s[i] = sin(th_i), c[i] = cos(th_i); ut has N-1 entries (already scaled by u_scale).
 // ---------------------------------------------------------------------------------------------
 template <int N>
 __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&s)[N],
                                                   const double (&c)[N], double gdx, double gdy,
-                                                  const double (&thd)[N], const double* u,
+                                                  const double (&thd)[N], const double* ut,
                                                   double& gddx, double& gddy, double (&thdd)[N]) {
-  // segment-centre velocities in the head frame, then shifted to the barycentric frame
-  double gx[N], gy[N];
+  // ts = thd*s, tc = thd*c: both the joint-velocity increments and the centripetal terms
+  double ts[N], tc[N], vx[N], vy[N];
   {
     double ax = 0.0, ay = 0.0, mx = 0.0, my = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double a = P.l * thd[i];
-      const double as = a * s[i], ac = a * c[i];
-      gx[i] = fma(-0.5, as, ax);
-      gy[i] = fma(0.5, ac, ay);
-      ax -= as;
-      ay += ac;
-      mx += gx[i];
-      my += gy[i];
+      ts[i] = thd[i] * s[i];
+      tc[i] = thd[i] * c[i];
+      vx[i] = fma(-0.5, ts[i], ax);  // segment centre, head frame, units of l
+      vy[i] = fma(0.5, tc[i], ay);
+      mx += vx[i];
+      my += vy[i];
+      if (i + 1 < N) { ax -= ts[i]; ay += tc[i]; }
     }
-    const double sx = fma(-P.inv_n, mx, gdx), sy = fma(-P.inv_n, my, gdy);
+    // barycentric frame: v_i += Gdot/l - mean
+    const double sx = fma(-P.inv_n, mx, gdx * P.inv_l), sy = fma(-P.inv_n, my, gdy * P.inv_l);
 #pragma unroll
-    for (int i = 0; i < N; ++i) { gx[i] += sx; gy[i] += sy; }
+    for (int i = 0; i < N; ++i) { vx[i] += sx; vy[i] += sy; }
   }
-  // friction force Phi_i = F_i n_i,  F_i = -k l (Gdot_i . n_i),  n_i = (-s, c)
-  double phx[N], phy[N], tau[N], wx[N], wy[N];
+  double psx[N], psy[N], tau[N], wx[N], wy[N];
   double sumx = 0.0, sumy = 0.0;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const double F = -P.kl * fma(gy[i], c[i], -gx[i] * s[i]);
-    phx[i] = -F * s[i];
-    phy[i] = F * c[i];
-    sumx += phx[i];
-    sumy += phy[i];
-    double t = P.tau_c * thd[i];
-    if (i >= 1) t += u[i - 1];
-    if (i <= N - 2) t -= u[i];
-    tau[i] = t;
-    const double al = P.six_over_l * t, be = P.half_lm * (thd[i] * thd[i]);
-    wx[i] = -fma(al, s[i], be * c[i]);
-    wy[i] = fma(al, c[i], -be * s[i]);
+    const double F = P.m2kappa * fma(vy[i], c[i], -vx[i] * s[i]);
+    psx[i] = -F * s[i];
+    psy[i] = F * c[i];
+    sumx += psx[i];
+    sumy += psy[i];
+    double du = 0.0;
+    if (i >= 1 && i <= N - 2) du = ut[i - 1] - ut[i];
+    else if (i >= 1) du = ut[i - 1];
+    else if (i <= N - 2) du = -ut[i];
+    tau[i] = fma(P.kappa, thd[i], du);
+    wx[i] = -fma(tau[i], s[i], thd[i] * tc[i]);
+    wy[i] = fma(tau[i], c[i], -thd[i] * ts[i]);
   }
-  gddx = sumx * P.inv_nm;
-  gddy = sumy * P.inv_nm;
+  gddx = sumx * P.gdd_c;
+  gddy = sumy * P.gdd_c;
 
-  // block-tridiagonal SPD system for the interior joint forces f_1..f_{N-1}
   constexpr int J = N - 1;
-  double fx[J + 2], fy[J + 2];  // f_0 .. f_N with f_0 = f_N = 0
-  fx[0] = fy[0] = 0.0;
-  fx[J + 1] = fy[J + 1] = 0.0;
+  double gx[J + 2], gy[J + 2];  // g_0 .. g_N with g_0 = g_N = 0
+  gx[0] = gy[0] = 0.0;
+  gx[J + 1] = gy[J + 1] = 0.0;
   if (J >= 1) {
+    double ss[N], sc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { ss[i] = s[i] * s[i]; sc[i] = s[i] * c[i]; }
     double Xa[J], Xb[J], Xd[J];  // inverse of the pivot block [[a,b],[b,d]]
     double rx[J], ry[J];         // eliminated right-hand side
-    double pa, pb, pd;           // current pivot block
 #pragma unroll
     for (int j = 1; j <= J; ++j) {
-      // segment j-1 and j meet at joint j
-      const double ss0 = s[j - 1] * s[j - 1], sc0 = s[j - 1] * c[j - 1], cc0 = c[j - 1] * c[j - 1];
-      const double ss1 = s[j] * s[j], sc1 = s[j] * c[j], cc1 = c[j] * c[j];
-      pa = fma(3.0, ss0 + ss1, 2.0);
-      pb = -3.0 * (sc0 + sc1);
-      pd = fma(3.0, cc0 + cc1, 2.0);
-      double r0 = (phx[j] - phx[j - 1]) - (wx[j - 1] + wx[j]);
-      double r1 = (phy[j] - phy[j - 1]) - (wy[j - 1] + wy[j]);
+      // segments j-1 and j meet at joint j;  cc = 1 - ss  =>  pd = 10 - pa,  qd = 1 - qa
+      double pa = fma(3.0, ss[j - 1] + ss[j], 2.0);
+      double pb = -3.0 * (sc[j - 1] + sc[j]);
+      double pd = 10.0 - pa;
+      double r0 = (psx[j] - psx[j - 1]) - (wx[j - 1] + wx[j]);
+      double r1 = (psy[j] - psy[j - 1]) - (wy[j - 1] + wy[j]);
       if (j >= 2) {
-        // Q_{j-1} = 3 N_{j-1} - I couples f_{j-1} and f_j
-        const double qa = fma(3.0, ss0, -1.0), qb = -3.0 * sc0, qd = fma(3.0, cc0, -1.0);
-        // T = Q X   (X = inverse of previous pivot)
+        const double qa = fma(3.0, ss[j - 1], -1.0), qb = -3.0 * sc[j - 1], qd = 1.0 - qa;
         const double t00 = fma(qa, Xa[j - 2], qb * Xb[j - 2]);
         const double t01 = fma(qa, Xb[j - 2], qb * Xd[j - 2]);
         const double t10 = fma(qb, Xa[j - 2], qd * Xb[j - 2]);
         const double t11 = fma(qb, Xb[j - 2], qd * Xd[j - 2]);
-        pa -= fma(t00, qa, t01 * qb);
-        pb -= fma(t00, qb, t01 * qd);
-        pd -= fma(t10, qb, t11 * qd);
-        r0 -= fma(t00, rx[j - 2], t01 * ry[j - 2]);
-        r1 -= fma(t10, rx[j - 2], t11 * ry[j - 2]);
+        pa = fma(-t01, qb, fma(-t00, qa, pa));
+        pb = fma(-t01, qd, fma(-t00, qb, pb));
+        pd = fma(-t11, qd, fma(-t10, qb, pd));
+        r0 = fma(-t01, ry[j - 2], fma(-t00, rx[j - 2], r0));
+        r1 = fma(-t11, ry[j - 2], fma(-t10, rx[j - 2], r1));
       }
       const double idet = fast_rcp(fma(pa, pd, -pb * pb));
       Xa[j - 1] = pd * idet;
@@ -142,20 +150,40 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
     for (int j = J; j >= 1; --j) {
       double y0 = rx[j - 1], y1 = ry[j - 1];
       if (j < J) {
-        const double qa = fma(3.0, s[j] * s[j], -1.0), qb = -3.0 * (s[j] * c[j]),
-                     qd = fma(3.0, c[j] * c[j], -1.0);
-        y0 -= fma(qa, fx[j + 1], qb * fy[j + 1]);
-        y1 -= fma(qb, fx[j + 1], qd * fy[j + 1]);
+        const double qa = fma(3.0, ss[j], -1.0), qb = -3.0 * sc[j], qd = 1.0 - qa;
+        y0 = fma(-qb, gy[j + 1], fma(-qa, gx[j + 1], y0));
+        y1 = fma(-qd, gy[j + 1], fma(-qb, gx[j + 1], y1));
       }
-      fx[j] = fma(Xa[j - 1], y0, Xb[j - 1] * y1);
-      fy[j] = fma(Xb[j - 1], y0, Xd[j - 1] * y1);
+      gx[j] = fma(Xa[j - 1], y0, Xb[j - 1] * y1);
+      gy[j] = fma(Xb[j - 1], y0, Xd[j - 1] * y1);
     }
   }
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const double vx = fx[i] + fx[i + 1], vy = fy[i] + fy[i + 1];
-    thdd[i] = fma(P.thdd_c, fma(c[i], vy, -s[i] * vx), tau[i] * P.inv_I);
+    const double ex = gx[i] + gx[i + 1], ey = gy[i] + gy[i + 1];
+    thdd[i] = fma(3.0, fma(c[i], ey, -s[i] * ex), tau[i]);
   }
+}
+
+// (cos, sin) of th + d from (cos, sin) of th for a small increment |d| <= 1/8: Taylor polynomials of
+// sin(d)/d and (cos(d)-1)/d^2 (truncation < 3e-17 relative), then one 2x2 rotation.  17 FP64
+// operations, no range reduction, no integer work -- against ~27 FP64 + ~50 other instructions for a
+// full double-precision sincos.
+__device__ __forceinline__ void rotate_small(double d, double& s, double& c) {
+  const double z = d * d;
+  double ps = fma(z, 2.7557319223985893e-06, -1.9841269841269841e-04);   // 1/9!, -1/7!
+  ps = fma(z, ps, 8.3333333333333332e-03);                                 // 1/5!
+  ps = fma(z, ps, -1.6666666666666666e-01);                                // -1/3!
+  const double sn = fma(d * z, ps, d);                                     // sin d
+  double pc = fma(z, -2.7557319223985888e-07, 2.4801587301587302e-05);   // -1/10!, 1/8!
+  pc = fma(z, pc, -1.3888888888888889e-03);                                // -1/6!
+  pc = fma(z, pc, 4.1666666666666664e-02);                                 // 1/4!
+  pc = fma(z, pc, -0.5);
+  const double cm1 = z * pc;                                               // cos d - 1
+  const double c2 = fma(-s, sn, fma(c, cm1, c));
+  const double s2 = fma(c, sn, fma(s, cm1, s));
+  c = c2;
+  s = s2;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -324,9 +352,10 @@ __device__ __forceinline__ void rlglue_accelerations(const Phys& P, const double
   }
 }
 
-// One integration step in registers.  VARIANT 0: explicit Euler (remy_swimmer_env.py:88-91),
-// VARIANT 1: semi-implicit Euler (SwimmerEnvironment.cpp:228-236).  Returns the reward
-// Gdot_new . direction (remy_swimmer_env.py:238-243 / cpp:273-277).
+// One integration step in registers with freshly evaluated sines/cosines (batched single step,
+// RL-Glue rollouts).  VARIANT 0: explicit Euler (remy_swimmer_env.py:88-91), VARIANT 1:
+// semi-implicit Euler (SwimmerEnvironment.cpp:228-236).  u = torques (unscaled, n-1 entries).
+// Returns the reward Gdot_new . direction (remy_swimmer_env.py:238-243 / cpp:273-277).
 template <int N, int VARIANT>
 __device__ __forceinline__ double swimmer_step(const Phys& P, double& gdx, double& gdy,
                                                double (&th)[N], double (&thd)[N],
@@ -335,8 +364,14 @@ __device__ __forceinline__ double swimmer_step(const Phys& P, double& gdx, doubl
 #pragma unroll
   for (int i = 0; i < N; ++i) sincos(th[i], &s[i], &c[i]);
   double gddx, gddy, thdd[N];
-  if (VARIANT == 0) gym_accelerations<N>(P, s, c, gdx, gdy, thd, u, gddx, gddy, thdd);
-  else rlglue_accelerations<N>(P, s, c, gdx, gdy, thd, u, gddx, gddy, thdd);
+  if (VARIANT == 0) {
+    double ut[N > 1 ? N - 1 : 1];
+#pragma unroll
+    for (int k = 0; k < N - 1; ++k) ut[k] = u[k] * P.u_scale;
+    gym_accelerations<N>(P, s, c, gdx, gdy, thd, ut, gddx, gddy, thdd);
+  } else {
+    rlglue_accelerations<N>(P, s, c, gdx, gdy, thd, u, gddx, gddy, thdd);
+  }
   gdx = fma(P.h, gddx, gdx);
   gdy = fma(P.h, gddy, gdy);
 #pragma unroll
@@ -348,6 +383,38 @@ __device__ __forceinline__ double swimmer_step(const Phys& P, double& gdx, doubl
       thd[i] = fma(P.h, thdd[i], thd[i]);
       th[i] = fma(P.h, thd[i], th[i]);
     }
+  }
+  return fma(gdx, P.dirx, gdy * P.diry);
+}
+
+// Rollout form of the gym step: (s, c) = (sin th, cos th) are carried in registers from step to
+// step and advanced by the rotation of the angle increment h*thd instead of being re-evaluated.
+// `resync` (warp-uniform; the rollout kernel sets it every 64th step) or an increment above 1/8 rad
+// on any segment re-evaluates them exactly from th.  ut = torques already scaled by P.u_scale.
+template <int N>
+__device__ __forceinline__ double gym_step_tracked(const Phys& P, double& gdx, double& gdy,
+                                                   double (&th)[N], double (&thd)[N],
+                                                   double (&s)[N], double (&c)[N],
+                                                   const double* ut, bool resync) {
+  double gddx, gddy, thdd[N];
+  gym_accelerations<N>(P, s, c, gdx, gdy, thd, ut, gddx, gddy, thdd);
+  gdx = fma(P.h, gddx, gdx);
+  gdy = fma(P.h, gddy, gdy);
+  double d[N];
+  bool exact = resync;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    d[i] = P.h * thd[i];
+    exact = exact || !(fabs(d[i]) <= 0.125);
+    th[i] = fma(P.h, thd[i], th[i]);
+    thd[i] = fma(P.h, thdd[i], thd[i]);
+  }
+  if (exact) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) sincos(th[i], &s[i], &c[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) rotate_small(d[i], s[i], c[i]);
   }
   return fma(gdx, P.dirx, gdy * P.diry);
 }

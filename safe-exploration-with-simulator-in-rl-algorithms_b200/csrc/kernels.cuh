@@ -79,8 +79,13 @@ step_kernel(Phys P, const double* __restrict__ state_in, const double* __restric
     double s[N], c[N], gddx, gddy, thdd[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) sincos(th[i], &s[i], &c[i]);
-    if (VARIANT == 0) gym_accelerations<N>(P, s, c, gdx, gdy, thd, u, gddx, gddy, thdd);
-    else rlglue_accelerations<N>(P, s, c, gdx, gdy, thd, u, gddx, gddy, thdd);
+    if (VARIANT == 0) {
+#pragma unroll
+      for (int a = 0; a < NA; ++a) u[a] *= P.u_scale;
+      gym_accelerations<N>(P, s, c, gdx, gdy, thd, u, gddx, gddy, thdd);
+    } else {
+      rlglue_accelerations<N>(P, s, c, gdx, gdy, thd, u, gddx, gddy, thdd);
+    }
     double* o = state_out + e * (N + 2);
     o[0] = gddx; o[1] = gddy;
 #pragma unroll
@@ -236,6 +241,18 @@ rollout_kernel(const RolloutArgs a) {
   double* traj = a.trajectory ? a.trajectory + e * NO : nullptr;
   const long long traj_step = a.B * NO;
 
+  // gym variant: sines/cosines live in registers across steps (see gym_step_tracked)
+  double sn[N], cs[N];
+  double ut[NA > 0 ? NA : 1];  // torques scaled by 12/(m l^2)
+  if (VARIANT == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) sincos(th[i], &sn[i], &cs[i]);
+    if (!LINEAR) {
+#pragma unroll
+      for (int k = 0; k < NA; ++k) ut[k] = u[k] * a.real.u_scale;
+    }
+  }
+
   for (int t = 0; t < steps; ++t) {
     if (LINEAR) {
       double obs[NO];
@@ -256,14 +273,19 @@ rollout_kernel(const RolloutArgs a) {
         }
         if (a.clip) acc = fmin(fmax(acc, -a.real.max_u), a.real.max_u);
         u[k] = acc;
+        if (VARIANT == 0) ut[k] = acc * a.real.u_scale;
       }
     }
     if (SCREEN) {
-      // Safe_ARS.isSafe (safe_ars/ars.py:111-122): one simulator step from the current state
-      double sgx = gdx, sgy = gdy, sth[N], sthd[N];
+      // Safe_ARS.isSafe (safe_ars/ars.py:111-122): one simulator step from the current state.  The
+      // cost only looks at the new angular velocities, and the simulator starts from the same
+      // angles, so it shares this step's sines/cosines and needs only its own accelerations.
+      double sut[NA > 0 ? NA : 1], sgddx, sgddy, sthdd[N], sthd[N];
 #pragma unroll
-      for (int i = 0; i < N; ++i) { sth[i] = th[i]; sthd[i] = thd[i]; }
-      swimmer_step<N, 0>(a.sim, sgx, sgy, sth, sthd, u);
+      for (int k = 0; k < NA; ++k) sut[k] = u[k] * a.sim.u_scale;
+      gym_accelerations<N>(a.sim, sn, cs, gdx, gdy, thd, sut, sgddx, sgddy, sthdd);
+#pragma unroll
+      for (int i = 0; i < N; ++i) sthd[i] = fma(a.sim.h, sthdd[i], thd[i]);
       if (!(cost_max_abs_thd<N>(sthd) <= a.sim_thresh)) {
         // unsafe: nothing advances, and since obs and policy never change it never will again
         // (safe_ars/ars.py:151-152) -- the remaining H-t steps are this state repeated.
@@ -279,7 +301,8 @@ rollout_kernel(const RolloutArgs a) {
         break;
       }
     }
-    ret += swimmer_step<N, VARIANT>(a.real, gdx, gdy, th, thd, u);
+    if (VARIANT == 0) ret += gym_step_tracked<N>(a.real, gdx, gdy, th, thd, sn, cs, ut, (t & 63) == 63);
+    else ret += swimmer_step<N, 1>(a.real, gdx, gdy, th, thd, u);
     if (SCREEN) viol += (cost_max_abs_thd<N>(thd) > a.real_thresh) ? 1 : 0;
     if (STATS) {
       double d;
