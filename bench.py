@@ -269,32 +269,41 @@ def run_b200(args):
     value = total_steps / t_dev_s
     e2e_value = total_steps / t_e2e_s
 
-    # ---- supplementary: ARS iterations/s on config[2] (n=5, V2, N=1024 directions, H=1000) ----
+    # ---- supplementary: ARS iterations/s (rollouts + NCCL exchange + ranking + update) ----
+    #   config[2]: ARS V2, n=5, 1,024 directions, H=1000  (2,048 envs in total: latency-bound)
+    #   config[4]: n=10, 4,096 directions x 2 x 128 rollouts = 1,048,576 envs, H=1000 (throughput-bound)
     ars = None
     if not args.no_ars:
-        p5 = S.make_params(n=5)
-        Ndir = 1024
-        eng = S.ArsEngine(p5, N=Ndir, b=Ndir, alpha=0.0075, nu=0.01, H=1000, v2=True,
-                          semantics=S.ARS_AGENT, seed=0, device=device)
-        for _ in range(2):
-            eng.run_iteration()
-        barrier()
-        K2 = 5
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(K2):
-            eng.run_iteration()
-        e1.record(stream)
-        barrier()
-        t_ars = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(t_ars, op=dist.ReduceOp.MAX)
-        t_ars_s = float(t_ars.cpu()[0]) * 1e-3
-        ars = {"workload": "config[2]: ARS V2, 5-segment swimmer, 1,024 directions (2,048 rollouts), H=1000, "
-                           "directions sharded over %d GPU(s), strong scaling" % world,
-               "iters_per_s": K2 / t_ars_s, "env_steps_per_s": K2 * 2 * Ndir * 1000 / t_ars_s,
-               "ms_per_iter": 1e3 * t_ars_s / K2, "iters_timed": K2,
-               "mean_return_last": float(eng.returns.mean().cpu())}
+        ars = []
+        for tag, n_, Ndir, R_, K2, desc in (
+                ("config[2]", 5, 1024, 1, 5, "ARS V2, 5-segment swimmer, 1,024 directions (2,048 rollouts), H=1000"),
+                ("config[4]", 10, 4096, 128, 2, "ARS V2, 10-segment swimmer, 4,096 directions x 2 x 128 rollouts "
+                                                "(1,048,576 envs, reset + 1e-2*U[0,1) starts), H=1000")):
+            if Ndir % world != 0:
+                continue
+            eng = S.ArsEngine(S.make_params(n=n_), N=Ndir, b=Ndir, alpha=0.0075, nu=0.01, H=1000, v2=True,
+                              semantics=S.ARS_AGENT, seed=0, device=device, rollouts_per_direction=R_,
+                              init_perturb=1e-2 if R_ > 1 else 0.0)
+            for _ in range(2 if R_ == 1 else 1):
+                eng.run_iteration()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(K2):
+                eng.run_iteration()
+            e1.record(stream)
+            barrier()
+            t_ars = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(t_ars, op=dist.ReduceOp.MAX)
+            t_ars_s = float(t_ars.cpu()[0]) * 1e-3
+            steps_per_iter = 2.0 * Ndir * R_ * 1000
+            ars.append({"workload": "%s: %s; directions sharded over %d GPU(s) (strong scaling)" % (tag, desc, world),
+                        "iters_per_s": K2 / t_ars_s, "env_steps_per_s": K2 * steps_per_iter / t_ars_s,
+                        "ms_per_iter": 1e3 * t_ars_s / K2, "iters_timed": K2,
+                        "roofline_frac_fp64": (K2 * steps_per_iter / t_ars_s / world) * W_REF_V2[n_] / 1e12 / fp64_peak_tflops,
+                        "mean_return_last": float(eng.returns.mean().cpu())})
+            del eng
 
     if rank == 0:
         cpu = None

@@ -11,7 +11,7 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswimmer_ars.so")
+LIB_PATH = os.environ.get("SWM_LIB_PATH", os.path.join(_HERE, "libswimmer_ars.so"))
 
 GYM, RLGLUE = 0, 1
 POLICY_FIXED_ACTION, POLICY_EXPLICIT, POLICY_PHILOX, POLICY_DELTAS = 0, 1, 2, 3

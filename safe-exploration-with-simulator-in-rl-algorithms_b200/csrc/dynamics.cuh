@@ -42,16 +42,14 @@ struct Phys {
   double I;          // m*l^2/12
 };
 
-// ~2-ulp reciprocal for well-scaled positive arguments (the 2x2 block determinants are >= 4):
-// hardware seed + two Newton steps, no special-case path.
+// ~1-ulp reciprocal for well-scaled positive arguments (the 2x2 block determinants are >= 4):
+// hardware seed (>= 20 bits) + one cubically convergent step x(1 + e + e^2), e = 1 - d x
+// (3 FMAs, residual e^3 < 2^-60), no special-case path.
 __device__ __forceinline__ double fast_rcp(double d) {
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-  double e = fma(-d, x, 1.0);
-  x = fma(x, e, x);
-  e = fma(-d, x, 1.0);
-  x = fma(x, e, x);
-  return x;
+  const double e = fma(-d, x, 1.0);
+  return fma(x, fma(e, e, e), x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -89,22 +87,31 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
 #pragma unroll
     for (int i = 0; i < N; ++i) { vx[i] += sx; vy[i] += sy; }
   }
-  double psx[N], psy[N], tau[N], wx[N], wy[N];
+  // per segment: F_i = -2 kappa (v_i.n_i), tau~_i, and the two combinations the joint equations need
+  //   A_i = psi_i - w^_i = (F - tau~) n_i + thd^2 p_i      (right-hand side of joint i,   i >= 1)
+  //   B_i = psi_i + w^_i = (F + tau~) n_i - thd^2 p_i      (right-hand side of joint i+1, i <= N-2)
+  double tau[N], Ax[N], Ay[N], Bx[N], By[N];
   double sumx = 0.0, sumy = 0.0;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const double F = P.m2kappa * fma(vy[i], c[i], -vx[i] * s[i]);
-    psx[i] = -F * s[i];
-    psy[i] = F * c[i];
-    sumx += psx[i];
-    sumy += psy[i];
+    sumx = fma(-F, s[i], sumx);
+    sumy = fma(F, c[i], sumy);
     double du = 0.0;
     if (i >= 1 && i <= N - 2) du = ut[i - 1] - ut[i];
     else if (i >= 1) du = ut[i - 1];
     else if (i <= N - 2) du = -ut[i];
     tau[i] = fma(P.kappa, thd[i], du);
-    wx[i] = -fma(tau[i], s[i], thd[i] * tc[i]);
-    wy[i] = fma(tau[i], c[i], -thd[i] * ts[i]);
+    if (i >= 1) {
+      const double a = F - tau[i];
+      Ax[i] = fma(-a, s[i], thd[i] * tc[i]);
+      Ay[i] = fma(a, c[i], thd[i] * ts[i]);
+    }
+    if (i <= N - 2) {
+      const double b = F + tau[i];
+      Bx[i] = -fma(b, s[i], thd[i] * tc[i]);
+      By[i] = fma(b, c[i], -thd[i] * ts[i]);
+    }
   }
   gddx = sumx * P.gdd_c;
   gddy = sumy * P.gdd_c;
@@ -125,8 +132,8 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
       double pa = fma(3.0, ss[j - 1] + ss[j], 2.0);
       double pb = -3.0 * (sc[j - 1] + sc[j]);
       double pd = 10.0 - pa;
-      double r0 = (psx[j] - psx[j - 1]) - (wx[j - 1] + wx[j]);
-      double r1 = (psy[j] - psy[j - 1]) - (wy[j - 1] + wy[j]);
+      double r0 = Ax[j] - Bx[j - 1];
+      double r1 = Ay[j] - By[j - 1];
       if (j >= 2) {
         const double qa = fma(3.0, ss[j - 1], -1.0), qb = -3.0 * sc[j - 1], qd = 1.0 - qa;
         const double t00 = fma(qa, Xa[j - 2], qb * Xb[j - 2]);
@@ -160,26 +167,37 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
   }
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const double ex = gx[i] + gx[i + 1], ey = gy[i] + gy[i + 1];
+    // free ends: g_0 = g_N = 0
+    const double ex = (i == 0) ? gx[1] : (i == N - 1) ? gx[N - 1] : gx[i] + gx[i + 1];
+    const double ey = (i == 0) ? gy[1] : (i == N - 1) ? gy[N - 1] : gy[i] + gy[i + 1];
     thdd[i] = fma(3.0, fma(c[i], ey, -s[i] * ex), tau[i]);
   }
 }
 
-// (cos, sin) of th + d from (cos, sin) of th for a small increment |d| <= 1/8: Taylor polynomials of
-// sin(d)/d and (cos(d)-1)/d^2 (truncation < 3e-17 relative), then one 2x2 rotation.  17 FP64
-// operations, no range reduction, no integer work -- against ~27 FP64 + ~50 other instructions for a
-// full double-precision sincos.
+// (sin, cos) of th + d from (sin, cos) of th for a small increment d: Taylor polynomials of sin d
+// and cos d - 1, then one 2x2 rotation -- no range reduction, no integer work (a full
+// double-precision sincos is ~27 FP64 + ~50 other instructions).
+//   LONG = false, |d| <= 1/32: sin to d^7, cos to d^6  (truncation < 2.5e-17)   12 FP64 operations
+//   LONG = true,  |d| <= 1/8 : sin to d^9, cos to d^10 (truncation < 3e-17)     17 FP64 operations
+constexpr double kRotateShort = 0.03125, kRotateLong = 0.125;
+template <bool LONG>
 __device__ __forceinline__ void rotate_small(double d, double& s, double& c) {
   const double z = d * d;
-  double ps = fma(z, 2.7557319223985893e-06, -1.9841269841269841e-04);   // 1/9!, -1/7!
-  ps = fma(z, ps, 8.3333333333333332e-03);                                 // 1/5!
-  ps = fma(z, ps, -1.6666666666666666e-01);                                // -1/3!
-  const double sn = fma(d * z, ps, d);                                     // sin d
-  double pc = fma(z, -2.7557319223985888e-07, 2.4801587301587302e-05);   // -1/10!, 1/8!
-  pc = fma(z, pc, -1.3888888888888889e-03);                                // -1/6!
-  pc = fma(z, pc, 4.1666666666666664e-02);                                 // 1/4!
+  double ps, pc;
+  if (LONG) {
+    ps = fma(z, 2.7557319223985893e-06, -1.9841269841269841e-04);  // 1/9!, -1/7!
+    ps = fma(z, ps, 8.3333333333333332e-03);                         // 1/5!
+    pc = fma(z, -2.7557319223985888e-07, 2.4801587301587302e-05);  // -1/10!, 1/8!
+    pc = fma(z, pc, -1.3888888888888889e-03);                        // -1/6!
+    pc = fma(z, pc, 4.1666666666666664e-02);                         // 1/4!
+  } else {
+    ps = fma(z, -1.9841269841269841e-04, 8.3333333333333332e-03);  // -1/7!, 1/5!
+    pc = fma(z, -1.3888888888888889e-03, 4.1666666666666664e-02);  // -1/6!, 1/4!
+  }
+  ps = fma(z, ps, -1.6666666666666666e-01);  // -1/3!
   pc = fma(z, pc, -0.5);
-  const double cm1 = z * pc;                                               // cos d - 1
+  const double sn = fma(d * z, ps, d);  // sin d
+  const double cm1 = z * pc;            // cos d - 1
   const double c2 = fma(-s, sn, fma(c, cm1, c));
   const double s2 = fma(c, sn, fma(s, cm1, s));
   c = c2;
@@ -401,20 +419,22 @@ __device__ __forceinline__ double gym_step_tracked(const Phys& P, double& gdx, d
   gdx = fma(P.h, gddx, gdx);
   gdy = fma(P.h, gddy, gdy);
   double d[N];
-  bool exact = resync;
+  double dmax = 0.0;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     d[i] = P.h * thd[i];
-    exact = exact || !(fabs(d[i]) <= 0.125);
+    dmax = fmax(dmax, fabs(d[i]));
     th[i] = fma(P.h, thd[i], th[i]);
     thd[i] = fma(P.h, thdd[i], thd[i]);
   }
-  if (exact) {
+  // Decided per lane from the lane's own data only, so that an environment's trajectory does not
+  // depend on which other environments share its warp.  NaN falls through to sincos.
+  if (resync || !(dmax <= kRotateLong)) {
 #pragma unroll
     for (int i = 0; i < N; ++i) sincos(th[i], &s[i], &c[i]);
   } else {
 #pragma unroll
-    for (int i = 0; i < N; ++i) rotate_small(d[i], s[i], c[i]);
+    for (int i = 0; i < N; ++i) rotate_small<true>(d[i], s[i], c[i]);
   }
   return fma(gdx, P.dirx, gdy * P.diry);
 }

@@ -11,10 +11,15 @@
 #include "dynamics.cuh"
 #include "philox.cuh"
 
+#ifndef SWM_ROLLOUT_MIN_BLOCKS
+#define SWM_ROLLOUT_MIN_BLOCKS 1  // CTAs/SM the register allocator must leave room for
+#endif
+
 namespace swm {
 
 constexpr int kStepBlock = 128;
 constexpr int kRolloutBlock = 64;  // threads per CTA of the rollout kernel (2 warps)
+constexpr int kRegPolicyMax = 32;  // largest policy (doubles) kept in registers: n <= 4
 
 // Where the per-environment policy lives during a rollout.
 enum WMode {
@@ -118,11 +123,11 @@ __device__ __forceinline__ double cost_max_abs_thd(const double (&thd)[N]) {
 // LINEAR: 0 fixed actions, 1 linear policy.  NORM: ARS V2 normalisation.  STATS: accumulate
 // shifted first/second moments of every visited state.  SCREEN: per-step simulator screening.
 template <int N, int VARIANT, int WMODE, bool NORM, bool STATS, bool SCREEN>
-__global__ void __launch_bounds__(kRolloutBlock)
+__global__ void __launch_bounds__(kRolloutBlock, SWM_ROLLOUT_MIN_BLOCKS)
 rollout_kernel(const RolloutArgs a) {
   constexpr int NO = 2 * N + 2, NA = N - 1, WS = NA * NO;
   constexpr bool LINEAR = (WMODE != W_NONE);
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
   const long long e0 = (long long)blockIdx.x * kRolloutBlock + tid;
   const bool active = e0 < a.B;
@@ -163,7 +168,14 @@ rollout_kernel(const RolloutArgs a) {
   // ---- policy ----
   double Wr[WMODE == W_REG ? WS : 1];
   double u[NA > 0 ? NA : 1];
-  double mu[NORM ? NO : 1];
+  // warp-uniform vectors (V2 mean, moment pivot) are read from shared memory every step instead of
+  // occupying 2(2n+2) registers per thread
+  __shared__ double s_mu[NORM ? NO : 1], s_piv[STATS ? NO : 1];
+  if (NORM || STATS) {
+    if (NORM && tid < NO) s_mu[tid] = a.mean[tid];
+    if (STATS && tid < NO) s_piv[tid] = a.stats_pivot[tid];
+    __syncthreads();
+  }
   double* sW = nullptr;  // W_SMEM_*: element j of this thread's policy at sW[j * wstride]
   int wstride = 1;
   if (WMODE == W_SMEM_THREAD) { sW = smem + tid; wstride = kRolloutBlock; }
@@ -214,20 +226,16 @@ rollout_kernel(const RolloutArgs a) {
         if (j + 1 < WS) sW[(j + 1) * wstride] = w1;
       }
     }
-    if (NORM) {
-#pragma unroll
-      for (int j = 0; j < NO; ++j) mu[j] = a.mean[j];
-    }
     if (WMODE == W_SMEM_GROUP) __syncwarp();
   } else {
 #pragma unroll
     for (int k = 0; k < NA; ++k) u[k] = a.actions[e * NA + k];
   }
 
-  double s1[STATS ? NO : 1], s2[STATS ? NO : 1], piv[STATS ? NO : 1];
+  double s1[STATS ? NO : 1], s2[STATS ? NO : 1];
   if (STATS) {
 #pragma unroll
-    for (int j = 0; j < NO; ++j) { s1[j] = 0.0; s2[j] = 0.0; piv[j] = a.stats_pivot[j]; }
+    for (int j = 0; j < NO; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
   }
 
   // reward-constraint safe exploration (ars_agent.py:144-159): a screened-out direction is never
@@ -261,15 +269,26 @@ rollout_kernel(const RolloutArgs a) {
       for (int i = 0; i < N; ++i) { obs[2 + 2 * i] = th[i]; obs[3 + 2 * i] = thd[i]; }
       if (NORM) {
 #pragma unroll
-        for (int j = 0; j < NO; ++j) obs[j] -= mu[j];
+        for (int j = 0; j < NO; ++j) obs[j] -= s_mu[j];
       }
 #pragma unroll
       for (int k = 0; k < NA; ++k) {
         double acc = 0.0;
+        if (WMODE == W_SMEM_GROUP) {
+          // warp-uniform policy: 16-byte broadcast loads, two coefficients per LDS
+          const double2* row = reinterpret_cast<const double2*>(sW + k * NO);
 #pragma unroll
-        for (int j = 0; j < NO; ++j) {
-          const double w = (WMODE == W_REG) ? Wr[k * NO + j] : sW[(k * NO + j) * wstride];
-          acc = fma(w, obs[j], acc);
+          for (int j = 0; j < NO / 2; ++j) {
+            const double2 w = row[j];
+            acc = fma(w.x, obs[2 * j], acc);
+            acc = fma(w.y, obs[2 * j + 1], acc);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NO; ++j) {
+            const double w = (WMODE == W_REG) ? Wr[k * NO + j] : sW[(k * NO + j) * wstride];
+            acc = fma(w, obs[j], acc);
+          }
         }
         if (a.clip) acc = fmin(fmax(acc, -a.real.max_u), a.real.max_u);
         u[k] = acc;
@@ -306,12 +325,12 @@ rollout_kernel(const RolloutArgs a) {
     if (SCREEN) viol += (cost_max_abs_thd<N>(thd) > a.real_thresh) ? 1 : 0;
     if (STATS) {
       double d;
-      d = gdx - piv[0]; s1[0] += d; s2[0] = fma(d, d, s2[0]);
-      d = gdy - piv[1]; s1[1] += d; s2[1] = fma(d, d, s2[1]);
+      d = gdx - s_piv[0]; s1[0] += d; s2[0] = fma(d, d, s2[0]);
+      d = gdy - s_piv[1]; s1[1] += d; s2[1] = fma(d, d, s2[1]);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        d = th[i] - piv[2 + 2 * i]; s1[2 + 2 * i] += d; s2[2 + 2 * i] = fma(d, d, s2[2 + 2 * i]);
-        d = thd[i] - piv[3 + 2 * i]; s1[3 + 2 * i] += d; s2[3 + 2 * i] = fma(d, d, s2[3 + 2 * i]);
+        d = th[i] - s_piv[2 + 2 * i]; s1[2 + 2 * i] += d; s2[2 + 2 * i] = fma(d, d, s2[2 + 2 * i]);
+        d = thd[i] - s_piv[3 + 2 * i]; s1[3 + 2 * i] += d; s2[3 + 2 * i] = fma(d, d, s2[3 + 2 * i]);
       }
     }
     if (traj && active) {

@@ -59,7 +59,7 @@ int launch_rollout_n(const RolloutArgs& a, const RolloutFlags& f, cudaStream_t s
     return f.variant == SWM_DYN_GYM ? launch_rollout_one<N, 0, W_NONE, false, false, false>(a, st)
                                     : launch_rollout_one<N, 1, W_NONE, false, false, false>(a, st);
   }
-  if constexpr (WS <= 48) {
+  if constexpr (WS <= kRegPolicyMax) {
     return launch_rollout_linear<N, W_REG>(a, f, st);
   } else {
     if (f.group_w) return launch_rollout_linear<N, W_SMEM_GROUP>(a, f, st);
