@@ -68,110 +68,100 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
                                                   const double (&c)[N], double gdx, double gdy,
                                                   const double (&thd)[N], const double* ut,
                                                   double& gddx, double& gddy, double (&thdd)[N]) {
-  // ts = thd*s, tc = thd*c: both the joint-velocity increments and the centripetal terms
-  double ts[N], tc[N], vx[N], vy[N];
-  {
-    double ax = 0.0, ay = 0.0, mx = 0.0, my = 0.0;
+  // Streaming formulation: apart from the factorisation (5 doubles per joint) everything is a
+  // rolling value, so the live state is O(N) with a small constant (registers, no local memory).
+  //
+  // pass 0 -- barycentric shift.  Head-frame centre velocity of segment i (units of l) is
+  //   v'_i = sum_{q<i} thd_q n_q + thd_i n_i / 2, so mean_i v'_i = sum_q (N-q-1/2)/N thd_q n_q.
+  double sx = gdx * P.inv_l, sy = gdy * P.inv_l;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      ts[i] = thd[i] * s[i];
-      tc[i] = thd[i] * c[i];
-      vx[i] = fma(-0.5, ts[i], ax);  // segment centre, head frame, units of l
-      vy[i] = fma(0.5, tc[i], ay);
-      mx += vx[i];
-      my += vy[i];
-      if (i + 1 < N) { ax -= ts[i]; ay += tc[i]; }
-    }
-    // barycentric frame: v_i += Gdot/l - mean
-    const double sx = fma(-P.inv_n, mx, gdx * P.inv_l), sy = fma(-P.inv_n, my, gdy * P.inv_l);
-#pragma unroll
-    for (int i = 0; i < N; ++i) { vx[i] += sx; vy[i] += sy; }
+  for (int q = 0; q < N; ++q) {
+    const double w = (N - q - 0.5) / N;
+    sx = fma(w * thd[q], s[q], sx);
+    sy = fma(-w * thd[q], c[q], sy);
   }
-  // per segment: F_i = -2 kappa (v_i.n_i), tau~_i, and the two combinations the joint equations need
-  //   A_i = psi_i - w^_i = (F - tau~) n_i + thd^2 p_i      (right-hand side of joint i,   i >= 1)
-  //   B_i = psi_i + w^_i = (F + tau~) n_i - thd^2 p_i      (right-hand side of joint i+1, i <= N-2)
-  double tau[N], Ax[N], Ay[N], Bx[N], By[N];
-  double sumx = 0.0, sumy = 0.0;
+  // pass 1 -- per segment: friction, right-hand sides, and the forward block elimination of the
+  // joint between segment i-1 and i.
+  constexpr int J = N - 1;
+  double Xa[J > 0 ? J : 1], Xb[J > 0 ? J : 1], Xd[J > 0 ? J : 1];  // inverse pivot blocks
+  double rx[J > 0 ? J : 1], ry[J > 0 ? J : 1];                     // eliminated right-hand sides
+  double ax = sx, ay = sy;          // velocity of the joint at the head of segment i
+  double sumx = 0.0, sumy = 0.0;    // sum_i F_i n_i
+  double Bpx = 0.0, Bpy = 0.0;      // B_{i-1}
+  double ssp = 0.0, scp = 0.0;      // s^2, s c of segment i-1
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const double F = P.m2kappa * fma(vy[i], c[i], -vx[i] * s[i]);
+    const double ts = thd[i] * s[i], tc = thd[i] * c[i];
+    const double vx = fma(-0.5, ts, ax), vy = fma(0.5, tc, ay);
+    if (i + 1 < N) { ax -= ts; ay += tc; }
+    const double F = P.m2kappa * fma(vy, c[i], -vx * s[i]);
     sumx = fma(-F, s[i], sumx);
     sumy = fma(F, c[i], sumy);
     double du = 0.0;
     if (i >= 1 && i <= N - 2) du = ut[i - 1] - ut[i];
     else if (i >= 1) du = ut[i - 1];
     else if (i <= N - 2) du = -ut[i];
-    tau[i] = fma(P.kappa, thd[i], du);
+    const double tau = fma(P.kappa, thd[i], du);
+    thdd[i] = tau;  // completed in pass 2
+    const double ss = s[i] * s[i], sc = s[i] * c[i];
     if (i >= 1) {
-      const double a = F - tau[i];
-      Ax[i] = fma(-a, s[i], thd[i] * tc[i]);
-      Ay[i] = fma(a, c[i], thd[i] * ts[i]);
-    }
-    if (i <= N - 2) {
-      const double b = F + tau[i];
-      Bx[i] = -fma(b, s[i], thd[i] * tc[i]);
-      By[i] = fma(b, c[i], -thd[i] * ts[i]);
-    }
-  }
-  gddx = sumx * P.gdd_c;
-  gddy = sumy * P.gdd_c;
-
-  constexpr int J = N - 1;
-  double gx[J + 2], gy[J + 2];  // g_0 .. g_N with g_0 = g_N = 0
-  gx[0] = gy[0] = 0.0;
-  gx[J + 1] = gy[J + 1] = 0.0;
-  if (J >= 1) {
-    double ss[N], sc[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) { ss[i] = s[i] * s[i]; sc[i] = s[i] * c[i]; }
-    double Xa[J], Xb[J], Xd[J];  // inverse of the pivot block [[a,b],[b,d]]
-    double rx[J], ry[J];         // eliminated right-hand side
-#pragma unroll
-    for (int j = 1; j <= J; ++j) {
-      // segments j-1 and j meet at joint j;  cc = 1 - ss  =>  pd = 10 - pa,  qd = 1 - qa
-      double pa = fma(3.0, ss[j - 1] + ss[j], 2.0);
-      double pb = -3.0 * (sc[j - 1] + sc[j]);
+      // A_i = psi_i - w^_i = (F - tau~) n_i + thd^2 p_i
+      const double a = F - tau;
+      const double Ax = fma(-a, s[i], thd[i] * tc), Ay = fma(a, c[i], thd[i] * ts);
+      // joint j = i: P_j = 2I + 3(N_{i-1} + N_i); cc = 1 - ss  =>  pd = 10 - pa, qd = 1 - qa
+      double pa = fma(3.0, ssp + ss, 2.0);
+      double pb = -3.0 * (scp + sc);
       double pd = 10.0 - pa;
-      double r0 = Ax[j] - Bx[j - 1];
-      double r1 = Ay[j] - By[j - 1];
-      if (j >= 2) {
-        const double qa = fma(3.0, ss[j - 1], -1.0), qb = -3.0 * sc[j - 1], qd = 1.0 - qa;
-        const double t00 = fma(qa, Xa[j - 2], qb * Xb[j - 2]);
-        const double t01 = fma(qa, Xb[j - 2], qb * Xd[j - 2]);
-        const double t10 = fma(qb, Xa[j - 2], qd * Xb[j - 2]);
-        const double t11 = fma(qb, Xb[j - 2], qd * Xd[j - 2]);
+      double r0 = Ax - Bpx, r1 = Ay - Bpy;
+      if (i >= 2) {
+        const double qa = fma(3.0, ssp, -1.0), qb = -3.0 * scp, qd = 1.0 - qa;  // Q_{i-1}
+        const double t00 = fma(qa, Xa[i - 2], qb * Xb[i - 2]);
+        const double t01 = fma(qa, Xb[i - 2], qb * Xd[i - 2]);
+        const double t10 = fma(qb, Xa[i - 2], qd * Xb[i - 2]);
+        const double t11 = fma(qb, Xb[i - 2], qd * Xd[i - 2]);
         pa = fma(-t01, qb, fma(-t00, qa, pa));
         pb = fma(-t01, qd, fma(-t00, qb, pb));
         pd = fma(-t11, qd, fma(-t10, qb, pd));
-        r0 = fma(-t01, ry[j - 2], fma(-t00, rx[j - 2], r0));
-        r1 = fma(-t11, ry[j - 2], fma(-t10, rx[j - 2], r1));
+        r0 = fma(-t01, ry[i - 2], fma(-t00, rx[i - 2], r0));
+        r1 = fma(-t11, ry[i - 2], fma(-t10, rx[i - 2], r1));
       }
       const double idet = fast_rcp(fma(pa, pd, -pb * pb));
-      Xa[j - 1] = pd * idet;
-      Xb[j - 1] = -pb * idet;
-      Xd[j - 1] = pa * idet;
-      rx[j - 1] = r0;
-      ry[j - 1] = r1;
+      Xa[i - 1] = pd * idet;
+      Xb[i - 1] = -pb * idet;
+      Xd[i - 1] = pa * idet;
+      rx[i - 1] = r0;
+      ry[i - 1] = r1;
     }
-#pragma unroll
-    for (int j = J; j >= 1; --j) {
-      double y0 = rx[j - 1], y1 = ry[j - 1];
-      if (j < J) {
-        const double qa = fma(3.0, ss[j], -1.0), qb = -3.0 * sc[j], qd = 1.0 - qa;
-        y0 = fma(-qb, gy[j + 1], fma(-qa, gx[j + 1], y0));
-        y1 = fma(-qd, gy[j + 1], fma(-qb, gx[j + 1], y1));
-      }
-      gx[j] = fma(Xa[j - 1], y0, Xb[j - 1] * y1);
-      gy[j] = fma(Xb[j - 1], y0, Xd[j - 1] * y1);
+    if (i <= N - 2) {
+      // B_i = psi_i + w^_i = (F + tau~) n_i - thd^2 p_i
+      const double b = F + tau;
+      Bpx = -fma(b, s[i], thd[i] * tc);
+      Bpy = fma(b, c[i], -thd[i] * ts);
     }
+    ssp = ss;
+    scp = sc;
   }
+  gddx = sumx * P.gdd_c;
+  gddy = sumy * P.gdd_c;
+  // pass 2 -- back substitution g_j = X_j (r'_j - Q_j g_{j+1}) and thdd_i = 3 n_i.(g_i+g_{i+1}) + tau~_i
+  double gnx = 0.0, gny = 0.0;  // g_{j+1}
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    // free ends: g_0 = g_N = 0
-    const double ex = (i == 0) ? gx[1] : (i == N - 1) ? gx[N - 1] : gx[i] + gx[i + 1];
-    const double ey = (i == 0) ? gy[1] : (i == N - 1) ? gy[N - 1] : gy[i] + gy[i + 1];
-    thdd[i] = fma(3.0, fma(c[i], ey, -s[i] * ex), tau[i]);
+  for (int j = J; j >= 1; --j) {
+    double y0 = rx[j - 1], y1 = ry[j - 1];
+    if (j < J) {
+      const double qa = fma(3.0, s[j] * s[j], -1.0), qb = -3.0 * (s[j] * c[j]), qd = 1.0 - qa;
+      y0 = fma(-qb, gny, fma(-qa, gnx, y0));
+      y1 = fma(-qd, gny, fma(-qb, gnx, y1));
+    }
+    const double gjx = fma(Xa[j - 1], y0, Xb[j - 1] * y1);
+    const double gjy = fma(Xb[j - 1], y0, Xd[j - 1] * y1);
+    // segment j lies between joints j and j+1
+    const double ex = (j == J) ? gjx : gjx + gnx, ey = (j == J) ? gjy : gjy + gny;
+    thdd[j] = fma(3.0, fma(c[j], ey, -s[j] * ex), thdd[j]);
+    gnx = gjx;
+    gny = gjy;
   }
+  if (J >= 1) thdd[0] = fma(3.0, fma(c[0], gny, -s[0] * gnx), thdd[0]);  // free head: g_0 = 0
 }
 
 // (sin, cos) of th + d from (sin, cos) of th for a small increment d: Taylor polynomials of sin d

@@ -20,6 +20,8 @@ namespace swm {
 constexpr int kStepBlock = 128;
 constexpr int kRolloutBlock = 64;  // threads per CTA of the rollout kernel (2 warps)
 constexpr int kRegPolicyMax = 32;  // largest policy (doubles) kept in registers: n <= 4
+constexpr int kRegStatsMaxObs = 16; // V2 moment accumulators stay in registers up to n = 7; above, they
+                                    // live in shared memory (one column per thread)
 
 // Where the per-environment policy lives during a rollout.
 enum WMode {
@@ -232,8 +234,18 @@ rollout_kernel(const RolloutArgs a) {
     for (int k = 0; k < NA; ++k) u[k] = a.actions[e * NA + k];
   }
 
-  double s1[STATS ? NO : 1], s2[STATS ? NO : 1];
-  if (STATS) {
+  constexpr bool STATS_SMEM = STATS && (NO > kRegStatsMaxObs);
+  constexpr bool STATS_REG = STATS && !STATS_SMEM;
+  double s1[STATS_REG ? NO : 1], s2[STATS_REG ? NO : 1];
+  // STATS_SMEM: accumulator j of this thread at sS[j * kRolloutBlock], j < 2*NO, after the policies
+  double* sS = smem + tid;
+  if (STATS_SMEM) {
+    if (WMODE == W_SMEM_THREAD) sS += WS * kRolloutBlock;
+    if (WMODE == W_SMEM_GROUP) sS += WS * (kRolloutBlock / 32);
+#pragma unroll
+    for (int j = 0; j < 2 * NO; ++j) sS[j * kRolloutBlock] = 0.0;
+  }
+  if (STATS_REG) {
 #pragma unroll
     for (int j = 0; j < NO; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
   }
@@ -293,6 +305,9 @@ rollout_kernel(const RolloutArgs a) {
         if (a.clip) acc = fmin(fmax(acc, -a.real.max_u), a.real.max_u);
         u[k] = acc;
         if (VARIANT == 0) ut[k] = acc * a.real.u_scale;
+        // shared-memory policies: keep at most one row of coefficients in flight, otherwise the
+        // scheduler hoists all (n-1)(2n+2) loads and spills
+        if (WMODE == W_SMEM_THREAD || WMODE == W_SMEM_GROUP) asm volatile("" ::: "memory");
       }
     }
     if (SCREEN) {
@@ -324,13 +339,20 @@ rollout_kernel(const RolloutArgs a) {
     else ret += swimmer_step<N, 1>(a.real, gdx, gdy, th, thd, u);
     if (SCREEN) viol += (cost_max_abs_thd<N>(thd) > a.real_thresh) ? 1 : 0;
     if (STATS) {
-      double d;
-      d = gdx - s_piv[0]; s1[0] += d; s2[0] = fma(d, d, s2[0]);
-      d = gdy - s_piv[1]; s1[1] += d; s2[1] = fma(d, d, s2[1]);
+      double x[NO];
+      x[0] = gdx; x[1] = gdy;
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        d = th[i] - s_piv[2 + 2 * i]; s1[2 + 2 * i] += d; s2[2 + 2 * i] = fma(d, d, s2[2 + 2 * i]);
-        d = thd[i] - s_piv[3 + 2 * i]; s1[3 + 2 * i] += d; s2[3 + 2 * i] = fma(d, d, s2[3 + 2 * i]);
+      for (int i = 0; i < N; ++i) { x[2 + 2 * i] = th[i]; x[3 + 2 * i] = thd[i]; }
+#pragma unroll
+      for (int j = 0; j < NO; ++j) {
+        const double d = x[j] - s_piv[j];
+        if (STATS_SMEM) {
+          sS[j * kRolloutBlock] += d;
+          sS[(NO + j) * kRolloutBlock] = fma(d, d, sS[(NO + j) * kRolloutBlock]);
+        } else {
+          s1[j] += d;
+          s2[j] = fma(d, d, s2[j]);
+        }
       }
     }
     if (traj && active) {
@@ -360,7 +382,9 @@ rollout_kernel(const RolloutArgs a) {
     __shared__ double red[kRolloutBlock / 32][2 * NO];
 #pragma unroll
     for (int j = 0; j < NO; ++j) {
-      double v1 = active ? s1[j] : 0.0, v2 = active ? s2[j] : 0.0;
+      double v1 = STATS_SMEM ? sS[j * kRolloutBlock] : s1[j];
+      double v2 = STATS_SMEM ? sS[(NO + j) * kRolloutBlock] : s2[j];
+      if (!active) { v1 = 0.0; v2 = 0.0; }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         v1 += __shfl_xor_sync(0xffffffffu, v1, off);

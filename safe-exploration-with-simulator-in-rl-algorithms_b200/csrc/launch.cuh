@@ -25,6 +25,7 @@ static int launch_rollout_one(const RolloutArgs& a, cudaStream_t st) {
   size_t smem = 0;
   if (WMODE == W_SMEM_THREAD) smem = sizeof(double) * WS * kRolloutBlock;
   if (WMODE == W_SMEM_GROUP) smem = sizeof(double) * WS * (kRolloutBlock / 32);
+  if (STATS && (2 * N + 2) > kRegStatsMaxObs) smem += sizeof(double) * 2 * (2 * N + 2) * kRolloutBlock;
   auto kern = rollout_kernel<N, VARIANT, WMODE, NORM, STATS, SCREEN>;
   if (smem > 48 * 1024) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
