@@ -34,6 +34,7 @@ struct Phys {
   double m2kappa;    // -2*k*l/m    (psi_i = m2kappa * (v_i.n_i) * n_i)
   double u_scale;    // 12/(m*l^2)  (torques enter as u/I)
   double gdd_c;      // l/(2n)      (Gdd = gdd_c * sum_i psi_i)
+  double h_gdd_c;    // h*l/(2n)    (Euler update of Gdot straight from sum_i psi_i)
   double inv_n;      // 1/n
   // rlglue variant
   double kl;         // k*l
@@ -52,6 +53,14 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return fma(x, fma(e, e, e), x);
 }
 
+// Hides a value from common-subexpression elimination (the compiler would otherwise keep 2N products
+// alive across the whole sweep to save 2N multiplies, and spill for long chains).
+__device__ __forceinline__ double opaque(double x) {
+  asm volatile("" : "+d"(x));
+  return x;
+}
+constexpr int kKeepTsTc = 7;
+
 // ---------------------------------------------------------------------------------------------
 // gym variant, non-dimensional O(n) form.  With v = Gdot_i / l, g_j = 2 f_j / (m l),
 // ut = u * 12/(m l^2), kappa = k l / m:
@@ -67,18 +76,26 @@ template <int N>
 __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&s)[N],
                                                   const double (&c)[N], double gdx, double gdy,
                                                   const double (&thd)[N], const double* ut,
-                                                  double& gddx, double& gddy, double (&thdd)[N]) {
+                                                  double& psx, double& psy, double (&thdd)[N]) {
+  // Outputs: thdd, and (psx, psy) = sum_i psi_i; the caller scales it (Gdd = gdd_c * sum).
   // Streaming formulation: apart from the factorisation (5 doubles per joint) everything is a
   // rolling value, so the live state is O(N) with a small constant (registers, no local memory).
   //
   // pass 0 -- barycentric shift.  Head-frame centre velocity of segment i (units of l) is
   //   v'_i = sum_{q<i} thd_q n_q + thd_i n_i / 2, so mean_i v'_i = sum_q (N-q-1/2)/N thd_q n_q.
+  // The weights are compile-time constants, so with ts = thd*s, tc = thd*c (needed by pass 1 anyway)
+  // the two sums are constant-operand FMAs.  Up to kKeepTsTc segments ts/tc stay in registers; for
+  // longer chains pass 1 recomputes them (2 multiplies) rather than holding 2N more doubles live.
+  constexpr bool KEEP = (N <= kKeepTsTc);
+  double tsa[KEEP ? N : 1], tca[KEEP ? N : 1];
   double sx = gdx * P.inv_l, sy = gdy * P.inv_l;
 #pragma unroll
   for (int q = 0; q < N; ++q) {
     const double w = (N - q - 0.5) / N;
-    sx = fma(w * thd[q], s[q], sx);
-    sy = fma(-w * thd[q], c[q], sy);
+    const double ts = thd[q] * s[q], tc = thd[q] * c[q];
+    if (KEEP) { tsa[q] = ts; tca[q] = tc; }
+    sx = fma(w, ts, sx);
+    sy = fma(-w, tc, sy);
   }
   // pass 1 -- per segment: friction, right-hand sides, and the forward block elimination of the
   // joint between segment i-1 and i.
@@ -91,7 +108,7 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
   double ssp = 0.0, scp = 0.0;      // s^2, s c of segment i-1
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const double ts = thd[i] * s[i], tc = thd[i] * c[i];
+    const double ts = KEEP ? tsa[i] : opaque(thd[i]) * s[i], tc = KEEP ? tca[i] : opaque(thd[i]) * c[i];
     const double vx = fma(-0.5, ts, ax), vy = fma(0.5, tc, ay);
     if (i + 1 < N) { ax -= ts; ay += tc; }
     const double F = P.m2kappa * fma(vy, c[i], -vx * s[i]);
@@ -141,8 +158,8 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
     ssp = ss;
     scp = sc;
   }
-  gddx = sumx * P.gdd_c;
-  gddy = sumy * P.gdd_c;
+  psx = sumx;
+  psy = sumy;
   // pass 2 -- back substitution g_j = X_j (r'_j - Q_j g_{j+1}) and thdd_i = 3 n_i.(g_i+g_{i+1}) + tau~_i
   double gnx = 0.0, gny = 0.0;  // g_{j+1}
 #pragma unroll
@@ -166,28 +183,31 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
 
 // (sin, cos) of th + d from (sin, cos) of th for a small increment d: Taylor polynomials of sin d
 // and cos d - 1, then one 2x2 rotation -- no range reduction, no integer work (a full
-// double-precision sincos is ~27 FP64 + ~50 other instructions).
-//   LONG = false, |d| <= 1/32: sin to d^7, cos to d^6  (truncation < 2.5e-17)   12 FP64 operations
-//   LONG = true,  |d| <= 1/8 : sin to d^9, cos to d^10 (truncation < 3e-17)     17 FP64 operations
+// double-precision sincos is ~27 FP64 + ~50 other instructions).  Two additive tiers:
+//   base, |d| <= 1/32: sin to d^5, cos to d^6     truncation <= 5.8e-15 at the limit and ~(32 d)^7 of
+//                                                 that below it (1e-19 at |thd| = 7 rad/s, h = 1e-3)
+//   tail, |d| <= 1/8 : + the d^7, d^9 terms of sin and the d^8, d^10 terms of cos (truncation < 3e-17)
+// The tail is added under a per-lane branch: a warp whose lanes are all slow skips it, a mixed warp
+// pays 8 more operations per segment, and no lane's result depends on its neighbours.  The rollout
+// kernel re-evaluates (s, c) exactly from th every 64th step, so truncation never accumulates over
+// more than 63 steps.
 constexpr double kRotateShort = 0.03125, kRotateLong = 0.125;
-template <bool LONG>
-__device__ __forceinline__ void rotate_small(double d, double& s, double& c) {
-  const double z = d * d;
-  double ps, pc;
-  if (LONG) {
-    ps = fma(z, 2.7557319223985893e-06, -1.9841269841269841e-04);  // 1/9!, -1/7!
-    ps = fma(z, ps, 8.3333333333333332e-03);                         // 1/5!
-    pc = fma(z, -2.7557319223985888e-07, 2.4801587301587302e-05);  // -1/10!, 1/8!
-    pc = fma(z, pc, -1.3888888888888889e-03);                        // -1/6!
-    pc = fma(z, pc, 4.1666666666666664e-02);                         // 1/4!
-  } else {
-    ps = fma(z, -1.9841269841269841e-04, 8.3333333333333332e-03);  // -1/7!, 1/5!
-    pc = fma(z, -1.3888888888888889e-03, 4.1666666666666664e-02);  // -1/6!, 1/4!
-  }
-  ps = fma(z, ps, -1.6666666666666666e-01);  // -1/3!
+__device__ __forceinline__ void small_sincos_base(double d, double& z, double& sn, double& cm1) {
+  z = d * d;
+  const double ps = fma(z, 8.3333333333333332e-03, -1.6666666666666666e-01);  // 1/5!, -1/3!
+  double pc = fma(z, -1.3888888888888889e-03, 4.1666666666666664e-02);        // -1/6!, 1/4!
   pc = fma(z, pc, -0.5);
-  const double sn = fma(d * z, ps, d);  // sin d
-  const double cm1 = z * pc;            // cos d - 1
+  sn = fma(d * z, ps, d);  // sin d
+  cm1 = z * pc;            // cos d - 1
+}
+__device__ __forceinline__ void small_sincos_tail(double d, double z, double& sn, double& cm1) {
+  const double z2 = z * z;
+  const double ts = fma(z, 2.7557319223985893e-06, -1.9841269841269841e-04);   // 1/9!, -1/7!
+  const double tc = fma(z, -2.7557319223985888e-07, 2.4801587301587302e-05);   // -1/10!, 1/8!
+  sn = fma(d * (z2 * z), ts, sn);
+  cm1 = fma(z2 * z2, tc, cm1);
+}
+__device__ __forceinline__ void rotate_by(double sn, double cm1, double& s, double& c) {
   const double c2 = fma(-s, sn, fma(c, cm1, c));
   const double s2 = fma(c, sn, fma(s, cm1, s));
   c = c2;
@@ -377,6 +397,8 @@ __device__ __forceinline__ double swimmer_step(const Phys& P, double& gdx, doubl
 #pragma unroll
     for (int k = 0; k < N - 1; ++k) ut[k] = u[k] * P.u_scale;
     gym_accelerations<N>(P, s, c, gdx, gdy, thd, ut, gddx, gddy, thdd);
+    gddx *= P.gdd_c;
+    gddy *= P.gdd_c;
   } else {
     rlglue_accelerations<N>(P, s, c, gdx, gdy, thd, u, gddx, gddy, thdd);
   }
@@ -400,14 +422,14 @@ __device__ __forceinline__ double swimmer_step(const Phys& P, double& gdx, doubl
 // `resync` (warp-uniform; the rollout kernel sets it every 64th step) or an increment above 1/8 rad
 // on any segment re-evaluates them exactly from th.  ut = torques already scaled by P.u_scale.
 template <int N>
-__device__ __forceinline__ double gym_step_tracked(const Phys& P, double& gdx, double& gdy,
-                                                   double (&th)[N], double (&thd)[N],
-                                                   double (&s)[N], double (&c)[N],
-                                                   const double* ut, bool resync) {
-  double gddx, gddy, thdd[N];
-  gym_accelerations<N>(P, s, c, gdx, gdy, thd, ut, gddx, gddy, thdd);
-  gdx = fma(P.h, gddx, gdx);
-  gdy = fma(P.h, gddy, gdy);
+__device__ __forceinline__ void gym_step_tracked(const Phys& P, double& gdx, double& gdy,
+                                                 double (&th)[N], double (&thd)[N],
+                                                 double (&s)[N], double (&c)[N],
+                                                 const double* ut, bool resync) {
+  double psx, psy, thdd[N];
+  gym_accelerations<N>(P, s, c, gdx, gdy, thd, ut, psx, psy, thdd);
+  gdx = fma(P.h_gdd_c, psx, gdx);
+  gdy = fma(P.h_gdd_c, psy, gdy);
   double d[N];
   double dmax = 0.0;
 #pragma unroll
@@ -419,14 +441,29 @@ __device__ __forceinline__ double gym_step_tracked(const Phys& P, double& gdx, d
   }
   // Decided per lane from the lane's own data only, so that an environment's trajectory does not
   // depend on which other environments share its warp.  NaN falls through to sincos.
+  double z[N], sn[N], cm1[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) small_sincos_base(d[i], z[i], sn[i], cm1[i]);
+#ifdef SWM_ANALYZE_TIER  // static SASS analysis of one fast path only (tools/fastpath_mix.sh); never shipped
+  if (SWM_ANALYZE_TIER == 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) small_sincos_tail(d[i], z[i], sn[i], cm1[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) rotate_by(sn[i], cm1[i], s[i], c[i]);
+  return;
+#endif
+  if (!(dmax <= kRotateShort)) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) small_sincos_tail(d[i], z[i], sn[i], cm1[i]);
+  }
   if (resync || !(dmax <= kRotateLong)) {
 #pragma unroll
     for (int i = 0; i < N; ++i) sincos(th[i], &s[i], &c[i]);
   } else {
 #pragma unroll
-    for (int i = 0; i < N; ++i) rotate_small<true>(d[i], s[i], c[i]);
+    for (int i = 0; i < N; ++i) rotate_by(sn[i], cm1[i], s[i], c[i]);
   }
-  return fma(gdx, P.dirx, gdy * P.diry);
 }
 
 }  // namespace swm

@@ -90,6 +90,8 @@ step_kernel(Phys P, const double* __restrict__ state_in, const double* __restric
 #pragma unroll
       for (int a = 0; a < NA; ++a) u[a] *= P.u_scale;
       gym_accelerations<N>(P, s, c, gdx, gdy, thd, u, gddx, gddy, thdd);
+      gddx *= P.gdd_c;
+      gddy *= P.gdd_c;
     } else {
       rlglue_accelerations<N>(P, s, c, gdx, gdy, thd, u, gddx, gddy, thdd);
     }
@@ -224,8 +226,13 @@ rollout_kernel(const RolloutArgs a) {
       for (int j = 0; j < WS; j += 2) {
         double w0, w1;
         make_pair(j, w0, w1);
-        sW[j * wstride] = w0;
-        if (j + 1 < WS) sW[(j + 1) * wstride] = w1;
+        if (WMODE == W_SMEM_GROUP) {  // [obs][action] (see the policy product in the step loop)
+          sW[(j % NO) * NA + j / NO] = w0;
+          if (j + 1 < WS) sW[((j + 1) % NO) * NA + (j + 1) / NO] = w1;
+        } else {
+          sW[j * wstride] = w0;
+          if (j + 1 < WS) sW[(j + 1) * wstride] = w1;
+        }
       }
     }
     if (WMODE == W_SMEM_GROUP) __syncwarp();
@@ -257,6 +264,7 @@ rollout_kernel(const RolloutArgs a) {
   const int steps = skipped ? 0 : a.H;
 
   double ret = skipped ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
+  double sgx = 0.0, sgy = 0.0;  // gym variant: sum_t Gdot_t
   int viol = 0, frozen = a.H;
   double* traj = a.trajectory ? a.trajectory + e * NO : nullptr;
   const long long traj_step = a.B * NO;
@@ -275,39 +283,36 @@ rollout_kernel(const RolloutArgs a) {
 
   for (int t = 0; t < steps; ++t) {
     if (LINEAR) {
-      double obs[NO];
-      obs[0] = gdx; obs[1] = gdy;
+      // action_k = sum_j W[k][j] * obs_j, observation-major: the NA accumulators advance together so
+      // that consecutive DFMAs share the obs_j operand (served by the operand-reuse cache: a DFMA
+      // with three fresh register sources issues every 3 cycles on B200, see profiles/r01b_summary.md)
+      // and only one (normalised) observation is live at a time.  Each action still sums j = 0..NO-1
+      // in order, exactly like np.matmul's row dot product in ars/environment.py:27-35.
+      double acc[NA > 0 ? NA : 1];
 #pragma unroll
-      for (int i = 0; i < N; ++i) { obs[2 + 2 * i] = th[i]; obs[3 + 2 * i] = thd[i]; }
-      if (NORM) {
+      for (int k = 0; k < NA; ++k) acc[k] = 0.0;
 #pragma unroll
-        for (int j = 0; j < NO; ++j) obs[j] -= s_mu[j];
+      for (int j = 0; j < NO; ++j) {
+        double x = (j == 0) ? gdx : (j == 1) ? gdy : ((j & 1) ? thd[(j - 3) / 2] : th[(j - 2) / 2]);
+        if (NORM) x -= s_mu[j];
+#pragma unroll
+        for (int k = 0; k < NA; ++k) {
+          double w;
+          if (WMODE == W_REG) w = Wr[k * NO + j];
+          else if (WMODE == W_SMEM_GROUP) w = sW[j * NA + k];  // warp-uniform broadcast, [obs][action]
+          else w = sW[(k * NO + j) * wstride];
+          acc[k] = fma(x, w, acc[k]);
+        }
+        // shared-memory policies: keep at most one column of coefficients in flight, otherwise the
+        // scheduler hoists all (n-1)(2n+2) loads and spills
+        if (WMODE == W_SMEM_THREAD || WMODE == W_SMEM_GROUP) asm volatile("" ::: "memory");
       }
 #pragma unroll
       for (int k = 0; k < NA; ++k) {
-        double acc = 0.0;
-        if (WMODE == W_SMEM_GROUP) {
-          // warp-uniform policy: 16-byte broadcast loads, two coefficients per LDS
-          const double2* row = reinterpret_cast<const double2*>(sW + k * NO);
-#pragma unroll
-          for (int j = 0; j < NO / 2; ++j) {
-            const double2 w = row[j];
-            acc = fma(w.x, obs[2 * j], acc);
-            acc = fma(w.y, obs[2 * j + 1], acc);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < NO; ++j) {
-            const double w = (WMODE == W_REG) ? Wr[k * NO + j] : sW[(k * NO + j) * wstride];
-            acc = fma(w, obs[j], acc);
-          }
-        }
-        if (a.clip) acc = fmin(fmax(acc, -a.real.max_u), a.real.max_u);
-        u[k] = acc;
-        if (VARIANT == 0) ut[k] = acc * a.real.u_scale;
-        // shared-memory policies: keep at most one row of coefficients in flight, otherwise the
-        // scheduler hoists all (n-1)(2n+2) loads and spills
-        if (WMODE == W_SMEM_THREAD || WMODE == W_SMEM_GROUP) asm volatile("" ::: "memory");
+        double v = acc[k];
+        if (a.clip) v = fmin(fmax(v, -a.real.max_u), a.real.max_u);
+        u[k] = v;
+        if (VARIANT == 0) ut[k] = v * a.real.u_scale;
       }
     }
     if (SCREEN) {
@@ -335,8 +340,15 @@ rollout_kernel(const RolloutArgs a) {
         break;
       }
     }
-    if (VARIANT == 0) ret += gym_step_tracked<N>(a.real, gdx, gdy, th, thd, sn, cs, ut, (t & 63) == 63);
-    else ret += swimmer_step<N, 1>(a.real, gdx, gdy, th, thd, u);
+    if (VARIANT == 0) {
+      // reward_t = Gdot_t . direction (remy_swimmer_env.py:238-243); the two components are summed
+      // separately and dotted with the direction once, after the loop
+      gym_step_tracked<N>(a.real, gdx, gdy, th, thd, sn, cs, ut, (t & 63) == 63);
+      sgx += gdx;
+      sgy += gdy;
+    } else {
+      ret += swimmer_step<N, 1>(a.real, gdx, gdy, th, thd, u);
+    }
     if (SCREEN) viol += (cost_max_abs_thd<N>(thd) > a.real_thresh) ? 1 : 0;
     if (STATS) {
       double x[NO];
@@ -363,6 +375,7 @@ rollout_kernel(const RolloutArgs a) {
     }
   }
 
+  if (VARIANT == 0) ret += fma(sgx, a.real.dirx, sgy * a.real.diry);
   if (active) {
     a.returns[e] = ret;
     if (a.final_state) {

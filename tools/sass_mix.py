@@ -18,7 +18,7 @@ def load(obj, pat):
     out = []
     for f in funcs[1:]:
         name = f.split("\n", 1)[0].strip()
-        if pat in name:
+        if re.search(pat, name):
             out.append((name, f))
     return out
 
@@ -61,6 +61,39 @@ def family(op, operands=""):
     return "other:" + op0
 
 
+def reuse_adjusted(rows, lo, hi):
+    """FP64 issue cycles of [lo, hi] with the measured B200 costs: DFMA with three vector-register
+    sources 3.1 cycles unless one of them sits in the operand-reuse cache (same register, same slot,
+    flagged .reuse by the preceding FP64 instruction), everything else ~2.1."""
+    cyc, n3, n3r = 0.0, 0, 0
+    prev = {}
+    for addr, ins in rows:
+        if not (lo <= addr <= hi):
+            continue
+        parts = ins.split()
+        k = 1 if parts[0].startswith("@") else 0
+        op0 = parts[k].split(".")[0]
+        if op0 not in ("DFMA", "DADD", "DMUL", "DSETP", "DMNMX"):
+            continue
+        srcs = [o.strip() for o in " ".join(parts[k + 1:]).split(",")][1:]
+        if op0 == "DSETP":
+            srcs = srcs[-3:]
+        regs = {}
+        for slot, o in enumerate(srcs):
+            m = re.match(r"^-?\|?(R\d+)", o)
+            if m:
+                regs[slot] = (m.group(1), ".reuse" in o)
+        if op0 == "DFMA" and len(regs) == 3:
+            n3 += 1
+            hit = any(prev.get(slot) == r for slot, (r, _) in regs.items())
+            n3r += hit
+            cyc += 2.2 if hit else 3.1
+        else:
+            cyc += 2.1
+        prev = {slot: r for slot, (r, flag) in regs.items() if flag}
+    return cyc, n3, n3r
+
+
 def main():
     obj, pat = sys.argv[1], sys.argv[2]
     for name, body in load(obj, pat):
@@ -87,6 +120,9 @@ def main():
                       for k, v in cnt.items() if k.startswith("fp64"))
             print("  loop 0x%x..0x%x: %d instructions, %d fp64 (%.0f%%), fp64 pipe cost %.0f cycles/iteration"
                   % (lo, hi, tot, fp64, 100.0 * fp64 / tot, cyc))
+            c2, n3, n3r = reuse_adjusted(rows, lo, hi)
+            print("  with operand reuse: %.0f cycles (%d of %d three-register DFMAs follow a .reuse of the same operand)"
+                  % (c2, n3r, n3))
             for k, v in sorted(cnt.items(), key=lambda kv: -kv[1])[:28]:
                 print("    %-28s %5d" % (k, v))
 
