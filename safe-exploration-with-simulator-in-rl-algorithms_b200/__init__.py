@@ -3,7 +3,7 @@
 Reference-shaped plugin surface (drop-in names):
     SwimmerEnv                      envs/gym_swimmer/swimmer/remy_swimmer_env.py
     Environment                     ars/environment.py
-    ARSAgent, EnvParam, ARSParam, Threshold, Database, Estimator     ars/*.py
+    ARSAgent, EnvParam, ARSParam, Threshold, Database, Estimator, Experiment     ars/*.py
     Basic_ARS, Safe_ARS             safe_ars/ars.py
 New batched surface: ops.step_batched / ops.rollout / ArsEngine (see include/swimmer_ars.h).
 All arithmetic runs in libswimmer_ars.so (hand-written sm_100a CUDA); there is no CPU fallback.
@@ -16,6 +16,7 @@ from .database import Database, pick_sub_database  # noqa: F401
 from .engine import ArsEngine  # noqa: F401
 from .environment import Environment  # noqa: F401
 from .estimator import Estimator  # noqa: F401
+from .experiment import Experiment, SeedFanout  # noqa: F401
 from .parameters import ARSParam, EnvParam, Threshold  # noqa: F401
 from .safe_ars import Basic_ARS, Safe_ARS, builtin_cost  # noqa: F401
 from .swimmer_env import SwimmerEnv  # noqa: F401

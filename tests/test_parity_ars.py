@@ -246,3 +246,26 @@ def test_estimator_objective(S, O):
         nxt, _ = O.step(p2, 0, traj[t], W @ traj[t])
         want += np.linalg.norm(nxt - traj[t + 1])
     assert abs(est.I(x) - want) < 1e-9 * want
+
+
+def test_seed_fanout_equals_sequential_agents(S, tmp_path):
+    """Seed fan-out (ars/experiment.py:64-72): S engines on S streams give, bit for bit, the curves
+    and policies of S agents trained one after the other; Experiment.plot keeps the call shape."""
+    p = S.make_params(n=3)
+    kw = dict(N=8, b=8, alpha=0.0075, nu=0.05, H=120, v2=True, semantics=S.ARS_AGENT)
+    fan = S.SeedFanout(p, range(5), **kw)
+    curves = fan.run(3)
+    assert curves.shape == (5, 4) and np.isfinite(curves).all()
+    for i, seed in enumerate(range(5)):
+        eng = S.ArsEngine(p, seed=seed, distributed=False, **kw)
+        want = [float(torch.nanmean(eng.run_iteration()).cpu()) for _ in range(4)]
+        np.testing.assert_array_equal(curves[i], want)
+        np.testing.assert_array_equal(fan.policies()[i], eng.policy_numpy())
+    assert len({tuple(c) for c in curves}) == 5  # different seeds, different curves
+    ep = S.EnvParam("LeonSwimmer", n=3, H=120, l_i=1., m_i=1., h=1e-3, k=10., epsilon=0)
+    ap = S.ARSParam("agent", V1=False, n_iter=3, H=120, N=8, b=8, alpha=0.0075, nu=0.05, safe=False,
+                    threshold=0, initial_w="Zero")
+    r_graphs = S.Experiment(ep, results_path=str(tmp_path) + "/").plot(5, ap)
+    np.testing.assert_array_equal(r_graphs, curves)
+    saved = list((tmp_path / "array").glob("*.npy"))
+    assert len(saved) == 1 and np.array_equal(np.load(saved[0]), r_graphs)
