@@ -33,7 +33,7 @@ extern "C" {
 #define SWM_API
 #endif
 
-#define SWM_ABI_VERSION 1
+#define SWM_ABI_VERSION 2
 #define SWM_MIN_SEGMENTS 2
 #define SWM_MAX_SEGMENTS 10
 
@@ -88,6 +88,10 @@ typedef struct {
   uint32_t dir0;       /* global index of this shard's first direction */
   int32_t dist;        /* swm_delta_dist */
   int32_t _pad;
+  const uint32_t* iteration_dev; /* optional DEVICE counter: the kernels use iteration + *iteration_dev.
+                                    Lets a captured CUDA graph of one ARS iteration be replayed: the
+                                    graph's arguments are frozen, the counter lives in device memory
+                                    and is advanced by swm_counter_add inside the graph. */
 } swm_philox_t;
 
 /* Per-step state-constraint screening (safe_ars/ars.py:111-153, Safe_ARS.isSafe/rollout) with the
@@ -225,6 +229,16 @@ SWM_API int swm_policy_actions(const swm_params_t* params, const double* obs, co
 /* Writes delta_k (k = dir0 .. dir0+count-1) into out[count, wsize]: lets tests and the host API
  * see exactly the perturbations the kernels use. */
 SWM_API int swm_philox_deltas(const swm_philox_t* philox, int count, int wsize, double* out, void* stream);
+
+/* *counter += inc on the stream (device uint32): the iteration counter of swm_philox_t.iteration_dev. */
+SWM_API int swm_counter_add(uint32_t* counter, uint32_t inc, void* stream);
+
+/* curve[min(*index, capacity-1)] = mean of the non-NaN entries of x[n] (NaN if there is none):
+ * the learning-curve entry of ARSAgent.runTraining (ars_agent.py:195-201: mean of the returns of the
+ * directions that were rolled out), recorded on the device so that a training loop never has to
+ * synchronise with the host.  index == NULL writes curve[0]. */
+SWM_API int swm_record_nanmean(const double* x, int n, double* curve, const uint32_t* index,
+                               uint32_t capacity, void* stream);
 
 /* FP64 pipe probe: every thread runs `iters` x 8 independent DFMA chains; returns through
  * *flops_out (host) the number of floating-point operations executed (2 per DFMA).  Used by

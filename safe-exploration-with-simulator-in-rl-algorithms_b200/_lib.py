@@ -18,6 +18,7 @@ POLICY_FIXED_ACTION, POLICY_EXPLICIT, POLICY_PHILOX, POLICY_DELTAS = 0, 1, 2, 3
 DELTA_PM1, DELTA_01 = 0, 1
 ARS_AGENT, ARS_TOPB, ARS_RLGLUE = 0, 1, 2
 MIN_SEGMENTS, MAX_SEGMENTS = 2, 10
+ABI_VERSION = 2  # include/swimmer_ars.h SWM_ABI_VERSION
 
 _dp = ctypes.c_void_p
 
@@ -30,7 +31,7 @@ class SwmParams(ctypes.Structure):
 
 class SwmPhilox(ctypes.Structure):
     _fields_ = [("seed", ctypes.c_uint64), ("iteration", ctypes.c_uint32), ("dir0", ctypes.c_uint32),
-                ("dist", ctypes.c_int32), ("_pad", ctypes.c_int32)]
+                ("dist", ctypes.c_int32), ("_pad", ctypes.c_int32), ("iteration_dev", _dp)]
 
 
 class SwmScreen(ctypes.Structure):
@@ -101,8 +102,10 @@ def lib():
     L.swm_policy_actions.argtypes = [pp, _dp, _dp, c_int, _dp, _dp, c_int, _dp, i64, _dp]
     L.swm_philox_deltas.argtypes = [ctypes.POINTER(SwmPhilox), c_int, c_int, _dp, _dp]
     L.swm_fp64_probe.argtypes = [c_int, c_int, c_int, _dp, ctypes.POINTER(dbl), _dp]
+    L.swm_counter_add.argtypes = [_dp, ctypes.c_uint32, _dp]
+    L.swm_record_nanmean.argtypes = [_dp, c_int, _dp, _dp, ctypes.c_uint32, _dp]
     L.swm_rlglue_set_params.argtypes = [pp]
-    if L.swm_abi_version() != 1:
+    if L.swm_abi_version() != ABI_VERSION:
         raise SwimmerLibError("ABI version mismatch")
     _lib = L
     return L

@@ -70,10 +70,11 @@ __global__ void __launch_bounds__(kArsBlock)
 ars_update_kernel(double* __restrict__ W, int wsize, const double* __restrict__ returns, int N,
                   const int* __restrict__ order, int n_order, const int* __restrict__ mask,
                   double divisor, int ddof, double alpha, uint64_t seed, uint32_t iteration,
-                  uint32_t dir0, int dist, const double* __restrict__ deltas,
-                  double* __restrict__ sigma_out) {
+                  const uint32_t* __restrict__ iter_dev, uint32_t dir0, int dist,
+                  const double* __restrict__ deltas, double* __restrict__ sigma_out) {
   __shared__ double red[kArsBlock / 32];
   const int tid = threadIdx.x;
+  if (iter_dev) iteration += *iter_dev;
   int used = min(n_order, N);
   if (mask) {  // only directions that were actually rolled out (sorted first by ars_rank_kernel)
     double c = 0.0;
@@ -159,8 +160,10 @@ __global__ void policy_actions_kernel(int n, double max_u, const double* __restr
   actions[idx] = acc;
 }
 
-__global__ void philox_deltas_kernel(uint64_t seed, uint32_t iteration, uint32_t dir0, int dist,
-                                     int count, int wsize, double* __restrict__ out) {
+__global__ void philox_deltas_kernel(uint64_t seed, uint32_t iteration, const uint32_t* iter_dev,
+                                     uint32_t dir0, int dist, int count, int wsize,
+                                     double* __restrict__ out) {
+  if (iter_dev) iteration += *iter_dev;
   const int pairs = (wsize + 1) / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)count * pairs) return;
@@ -250,6 +253,28 @@ __global__ void fp64_probe_kernel(int iters, double* __restrict__ sink) {
   if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
 }
 
+__global__ void counter_add_kernel(uint32_t* counter, uint32_t inc) { *counter += inc; }
+
+// mean of the non-NaN entries, fixed-order block reduction (one CTA)
+__global__ void __launch_bounds__(kArsBlock)
+record_nanmean_kernel(const double* __restrict__ x, int n, double* __restrict__ curve,
+                      const uint32_t* __restrict__ index, uint32_t capacity) {
+  __shared__ double red[kArsBlock / 32];
+  double s = 0.0, c = 0.0;
+  for (int i = threadIdx.x; i < n; i += kArsBlock) {
+    const double v = x[i];
+    if (v == v) { s += v; c += 1.0; }
+  }
+  s = block_sum(s, red);
+  __syncthreads();
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) {
+    uint32_t at = index ? *index : 0u;
+    if (at >= capacity) at = capacity - 1;
+    curve[at] = (c > 0.0) ? s / c : __longlong_as_double(0x7ff8000000000000LL);
+  }
+}
+
 }  // namespace swm
 
 using namespace swm;
@@ -283,8 +308,8 @@ extern "C" int swm_ars_update(double* W, int wsize, const double* returns, int N
   const uint32_t it = philox ? philox->iteration : 0, d0 = philox ? philox->dir0 : 0;
   const int dist = philox ? philox->dist : 0;
   ars_update_kernel<<<(wsize + 1) / 2, kArsBlock, 0, (cudaStream_t)stream>>>(
-      W, wsize, returns, N, order, n_order, mask, divisor, ddof, alpha, seed, it, d0, dist, deltas,
-      sigma_out);
+      W, wsize, returns, N, order, n_order, mask, divisor, ddof, alpha, seed, it,
+      philox ? philox->iteration_dev : nullptr, d0, dist, deltas, sigma_out);
   return SWM_CHECK_LAUNCH();
 }
 
@@ -314,7 +339,7 @@ extern "C" int swm_philox_deltas(const swm_philox_t* philox, int count, int wsiz
   if (!philox || !out || count < 1 || wsize < 1) return SWM_ERR_BAD_ARG;
   const long long total = (long long)count * ((wsize + 1) / 2);
   philox_deltas_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      philox->seed, philox->iteration, philox->dir0, philox->dist, count, wsize, out);
+      philox->seed, philox->iteration, philox->iteration_dev, philox->dir0, philox->dist, count, wsize, out);
   return SWM_CHECK_LAUNCH();
 }
 
@@ -353,5 +378,18 @@ extern "C" int swm_fp64_probe(int blocks, int threads, int iters, double* sink, 
   if (blocks < 1 || threads < 1 || threads > 1024 || iters < 1 || !sink) return SWM_ERR_BAD_ARG;
   fp64_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
   if (flops_out) *flops_out = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+  return SWM_CHECK_LAUNCH();
+}
+
+extern "C" int swm_counter_add(uint32_t* counter, uint32_t inc, void* stream) {
+  if (!counter) return SWM_ERR_BAD_ARG;
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);
+  return SWM_CHECK_LAUNCH();
+}
+
+extern "C" int swm_record_nanmean(const double* x, int n, double* curve, const uint32_t* index,
+                                  uint32_t capacity, void* stream) {
+  if (!x || !curve || n < 1 || capacity < 1) return SWM_ERR_BAD_ARG;
+  record_nanmean_kernel<<<1, kArsBlock, 0, (cudaStream_t)stream>>>(x, n, curve, index, capacity);
   return SWM_CHECK_LAUNCH();
 }

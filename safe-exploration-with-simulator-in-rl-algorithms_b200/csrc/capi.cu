@@ -180,6 +180,7 @@ extern "C" int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg,
   a.nu = cfg->nu;
   a.seed = cfg->philox.seed;
   a.iteration = cfg->philox.iteration;
+  a.iter_dev = cfg->philox.iteration_dev;
   a.dir0 = cfg->philox.dir0;
   a.dist = cfg->philox.dist;
   a.mean = cfg->mean;

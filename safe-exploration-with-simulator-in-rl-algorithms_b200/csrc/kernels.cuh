@@ -47,6 +47,7 @@ struct RolloutArgs {
   double init_perturb;
   unsigned long long seed;
   unsigned int iteration, dir0;
+  const unsigned int* iter_dev;  // optional device counter added to `iteration`
   int dist;
   const double* mean;
   const double* inv_sigma;
@@ -137,6 +138,8 @@ rollout_kernel(const RolloutArgs a) {
   const bool active = e0 < a.B;
   const long long e = active ? e0 : a.B - 1;  // idle lanes shadow the last env, never store
 
+  const unsigned int iteration = a.iteration + (a.iter_dev ? *a.iter_dev : 0u);
+
   // ---- initial state ----
   double gdx, gdy, th[N], thd[N];
   if (a.init_state) {
@@ -162,7 +165,7 @@ rollout_kernel(const RolloutArgs a) {
 #pragma unroll
     for (int j = 0; j < NO; j += 2) {
       double d0, d1;
-      philox_delta_pair(a.seed, a.iteration, r, 1u, (uint32_t)(j >> 1), SWM_DELTA_UNIFORM_01, d0, d1);
+      philox_delta_pair(a.seed, iteration, r, 1u, (uint32_t)(j >> 1), SWM_DELTA_UNIFORM_01, d0, d1);
       if (j == 0) { gdx = fma(a.init_perturb, d0, gdx); gdy = fma(a.init_perturb, d1, gdy); }
       else { th[(j - 2) / 2] = fma(a.init_perturb, d0, th[(j - 2) / 2]);
              thd[(j - 2) / 2] = fma(a.init_perturb, d1, thd[(j - 2) / 2]); }
@@ -199,7 +202,7 @@ rollout_kernel(const RolloutArgs a) {
       if (philox || from_mem) {
         double d0, d1 = 0.0;
         if (philox) {
-          philox_delta_pair(a.seed, a.iteration, dir, 0u, (uint32_t)(j >> 1), a.dist, d0, d1);
+          philox_delta_pair(a.seed, iteration, dir, 0u, (uint32_t)(j >> 1), a.dist, d0, d1);
         } else {
           d0 = dmem[j];
           if (j + 1 < WS) d1 = dmem[j + 1];

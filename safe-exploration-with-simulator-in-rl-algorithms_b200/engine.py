@@ -11,6 +11,11 @@ One iteration =
 
 Directions are sharded contiguously across ranks (rank r owns [r N/world, (r+1) N/world)); the
 delta tensors never move.  Nothing in an iteration synchronises with the host.
+
+The iteration number that keys Philox lives in device memory (`iter_dev`, advanced by
+swm_counter_add at the end of the update), so the whole iteration is a fixed sequence of launches
+with fixed arguments: `use_graph=True` captures it once into a CUDA graph and replays it (one
+launch per iteration instead of ~10; with world > 1 the NCCL all-gather is captured with it).
 """
 import torch
 import torch.distributed as dist
@@ -24,7 +29,7 @@ class ArsEngine:
                  rollouts_per_direction=1, seed=0, variant=GYM, delta_dist=DELTA_PM1,
                  clip_actions=False, init_perturb=0.0, initial_policy=None, group=None,
                  distributed=None, device=None, sim_params=None, sim_threshold=None,
-                 step_screen=None):
+                 step_screen=None, use_graph=False, curve_capacity=0):
         _lib.require_cuda()
         self.params, self.N, self.b, self.alpha, self.nu, self.H = params, int(N), int(b), alpha, nu, int(H)
         self.v2, self.semantics, self.R = bool(v2), semantics, int(rollouts_per_direction)
@@ -47,7 +52,13 @@ class ArsEngine:
         self.W = torch.zeros(self.ws, **f64)
         if initial_policy is not None:
             self.W.copy_(torch.as_tensor(initial_policy, dtype=torch.float64).reshape(-1))
-        self.iteration = 0
+        self.iteration = 0  # host mirror of iter_dev
+        self.iter_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # optional device-side learning curve: curve[j] = nanmean(returns of iteration j)
+        self.curve = torch.full((int(curve_capacity),), float("nan"), **f64) if curve_capacity > 0 else None
+        self.use_graph = bool(use_graph)
+        self._graph = None
+        self._warm = False
         # V2 running statistics: record = [count, mean[F], M2[F]]; mean=0 / sigma=1 until the first
         # update (ars_agent.py:87-90)
         self.stats = torch.zeros(1 + 2 * self.no, **f64)
@@ -83,7 +94,7 @@ class ArsEngine:
         return ops.rollout(
             params, self.H, B=self.B_local, variant=self.variant, base_policy=self.W, nu=self.nu,
             deltas=deltas_local, dir_mask=dir_mask, init_perturb=self.init_perturb, seed=self.seed,
-            iteration=self.iteration, dir0=self.dir0, delta_dist=self.delta_dist,
+            iteration=0, iteration_dev=self.iter_dev, dir0=self.dir0, delta_dist=self.delta_dist,
             rollouts_per_policy=self.R, mean=self.mean if self.v2 else None,
             inv_sigma=self.inv_sigma if self.v2 else None, clip_actions=self.clip,
             stats_pivot=self.pivot if want_stats else None, want_trajectory=want_trajectory,
@@ -93,6 +104,26 @@ class ArsEngine:
         """One ARS iteration.  `deltas` ([N, ws] device tensor): use these perturbations instead of
         Philox (replaying the reference's numpy draws).  Returns the device tensor of all 2N
         per-policy returns (NaN for screened-out directions); never synchronises."""
+        plain = deltas is None and not want_trajectory and update
+        if self.use_graph and plain:
+            if not self._warm:
+                # first iteration eagerly: sizes the scratch buffers and sets kernel attributes
+                self._warm = True
+            elif self._graph is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(None, False, True)
+                self._graph = g
+            if self._graph is not None:
+                self._graph.replay()
+                self.iteration += 1
+                return self.returns
+        out = self._enqueue(deltas, want_trajectory, update)
+        if update:
+            self.iteration += 1
+        return out
+
+    def _enqueue(self, deltas, want_trajectory, update):
         Nl, R = self.N_local, self.R
         deltas_local = None if deltas is None else deltas.reshape(self.N, self.ws)[self.dir0:self.dir0 + Nl]
         dir_mask = None
@@ -105,6 +136,8 @@ class ArsEngine:
         res = self._rollouts(self.params, self._out, deltas_local, dir_mask, self.v2, want_trajectory,
                              self.step_screen)
         self.last = res
+        if res.stats_partial is not None:
+            self._out["stats_partial"] = res.stats_partial  # reuse: iterations allocate nothing
         rec = self._record
         if R == 1:
             rec[:2 * Nl].copy_(res.returns)
@@ -127,21 +160,28 @@ class ArsEngine:
             if self.mask is not None:
                 self.mask.copy_(self.mask_local)
         if update:
-            self.apply_update(deltas)
+            self._enqueue_update(deltas)
         return self.returns
 
     def apply_update(self, deltas=None):
+        """Ranking + update + statistics merge for the returns of the last `run_iteration(update=False)`."""
+        self._enqueue_update(deltas)
+        self.iteration += 1
+
+    def _enqueue_update(self, deltas=None):
         use_order, n_order, divisor, ddof = ops.update_args(self.semantics, self.N, self.b)
         order = None
         if use_order:
             order = ops.ars_topb(self.returns, self.mask, out=self.order)
         ops.ars_update(self.W, self.returns, self.N, order=order, n_order=n_order, divisor=divisor,
-                       ddof=ddof, alpha=self.alpha, seed=self.seed, iteration=self.iteration, dir0=0,
+                       ddof=ddof, alpha=self.alpha, seed=self.seed, iteration=0, iteration_dev=self.iter_dev, dir0=0,
                        delta_dist=self.delta_dist, deltas=deltas, mask=self.mask if use_order else None,
                        sigma_out=self.sigma)
         if self.v2:
             ops.stats_merge(self.stats, self._records, self.mean, self.inv_sigma)
-        self.iteration += 1
+        if self.curve is not None:
+            ops.record_nanmean(self.returns, self.curve, self.iter_dev)
+        ops.counter_add(self.iter_dev, 1)
 
     # ---- host views ----
     def policy_numpy(self):
@@ -159,7 +199,10 @@ class ArsEngine:
 
     def load_state_dict(self, sd):
         self.W.copy_(torch.as_tensor(sd["W"]))
+        if int(sd["seed"]) != self.seed and self._graph is not None:
+            self._graph = None  # the seed is a frozen kernel argument of the captured graph
         self.iteration, self.seed = int(sd["iteration"]), int(sd["seed"])
+        self.iter_dev.fill_(self.iteration)
         self.stats.copy_(torch.as_tensor(sd["stats"]))
         self.mean.copy_(torch.as_tensor(sd["mean"]))
         self.inv_sigma.copy_(torch.as_tensor(sd["inv_sigma"]))

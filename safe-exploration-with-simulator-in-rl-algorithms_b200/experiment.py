@@ -21,10 +21,12 @@ from .engine import ArsEngine
 
 
 class SeedFanout:
-    def __init__(self, params, seeds, *, device=None, **engine_kwargs):
+    def __init__(self, params, seeds, *, device=None, max_iterations=4096, use_graph=True, **engine_kwargs):
         """`seeds`: iterable of ints; `engine_kwargs`: everything `ArsEngine` takes except `seed`
         (N, b, alpha, nu, H, v2, semantics, sim_params, ...).  Always single-process
-        (`distributed=False`): the seeds are the parallel dimension."""
+        (`distributed=False`): the seeds are the parallel dimension.  Every engine records its
+        learning curve on the device (`max_iterations` entries) and, with `use_graph`, replays one
+        captured CUDA graph per iteration, so a round over all seeds costs one launch per seed."""
         _lib.require_cuda()
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda", torch.cuda.current_device())
@@ -33,6 +35,9 @@ class SeedFanout:
             raise ValueError("at least one seed")
         engine_kwargs = dict(engine_kwargs)
         engine_kwargs["distributed"] = False
+        engine_kwargs["use_graph"] = use_graph
+        engine_kwargs["curve_capacity"] = int(max_iterations)
+        self.max_iterations = int(max_iterations)
         self.streams, self.engines = [], []
         for s in self.seeds:
             st = torch.cuda.Stream(device=self.device)
@@ -48,22 +53,23 @@ class SeedFanout:
         directions that were rolled out, or the previous entry when every direction was screened
         out (ars_agent.py:195-201).  One host synchronisation, at the end."""
         total = n_iter + (1 if include_initial else 0)
+        start = self.engines[0].iteration
+        if start + total > self.max_iterations:
+            raise ValueError("max_iterations=%d is too small for %d more iterations" % (self.max_iterations, total))
         cur = torch.cuda.current_stream(self.device)
-        curves = torch.full((len(self.engines), total), float("nan"), dtype=torch.float64, device=self.device)
         for st in self.streams:
             st.wait_stream(cur)
         for j in range(total):
-            for i, (eng, st) in enumerate(zip(self.engines, self.streams)):
+            for eng, st in zip(self.engines, self.streams):
                 with torch.cuda.stream(st):
-                    ret = eng.run_iteration()
-                    curves[i, j] = torch.nanmean(ret)
+                    eng.run_iteration()
         for st in self.streams:
             cur.wait_stream(st)
-        out = curves.cpu().numpy()
-        for row in out:  # all directions screened out -> previous value
-            for j in range(1, total):
+        out = torch.stack([e.curve[start:start + total] for e in self.engines]).cpu().numpy()
+        for i, row in enumerate(out):  # all directions screened out -> previous value
+            for j in range(total):
                 if np.isnan(row[j]):
-                    row[j] = row[j - 1]
+                    row[j] = row[j - 1] if j > 0 else (self._curves[i][-1] if self._curves is not None else np.nan)
         self._curves = out
         return out
 

@@ -14,7 +14,7 @@ from ._lib import (ARS_AGENT, ARS_RLGLUE, ARS_TOPB, DELTA_01, DELTA_PM1, GYM, PO
                    POLICY_EXPLICIT, POLICY_FIXED_ACTION, POLICY_PHILOX, RLGLUE)
 
 __all__ = ["step_batched", "accelerations_batched", "rollout", "RolloutResult", "philox_deltas",
-           "ars_topb", "ars_update", "stats_finalize", "stats_merge", "reduce_returns", "screen_mask", "policy_actions", "update_args",
+           "ars_topb", "ars_update", "counter_add", "record_nanmean", "stats_finalize", "stats_merge", "reduce_returns", "screen_mask", "policy_actions", "update_args",
            "fp64_probe", "obs_dim", "act_dim", "policy_size", "reset_state"]
 
 
@@ -90,7 +90,7 @@ class RolloutResult:
 
 def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base_policy=None, nu=0.0,
             deltas=None, dir_mask=None, init_perturb=0.0,
-            seed=0, iteration=0, dir0=0, delta_dist=DELTA_PM1, rollouts_per_policy=1, mean=None,
+            seed=0, iteration=0, iteration_dev=None, dir0=0, delta_dist=DELTA_PM1, rollouts_per_policy=1, mean=None,
             inv_sigma=None, clip_actions=False, init_state=None, want_final=False,
             want_trajectory=False, stats_pivot=None, screen=None, out=None, device=None):
     """One fused H-step rollout of B environments (swm_rollout).
@@ -152,6 +152,7 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
     cfg.init_perturb = float(init_perturb)
     cfg.philox.seed, cfg.philox.iteration = int(seed) & (2 ** 64 - 1), int(iteration)
     cfg.philox.dir0, cfg.philox.dist = int(dir0), int(delta_dist)
+    cfg.philox.iteration_dev = _counter_ptr(iteration_dev)
     if (mean is None) != (inv_sigma is None):
         raise ValueError("mean and inv_sigma go together")
     if mean is not None:
@@ -203,17 +204,43 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
     return res
 
 
-def _philox(seed, iteration, dir0, dist):
+def _counter_ptr(t):
+    """Device iteration counter: one int32 CUDA element (read as uint32 by the kernels)."""
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.int32 and t.numel() == 1):
+        raise ValueError("iteration_dev must be a CUDA int32 tensor with one element")
+    return t.data_ptr()
+
+
+def _philox(seed, iteration, dir0, dist, iteration_dev=None):
     p = _lib.SwmPhilox()
     p.seed, p.iteration, p.dir0, p.dist = int(seed) & (2 ** 64 - 1), int(iteration), int(dir0), int(dist)
+    p.iteration_dev = _counter_ptr(iteration_dev)
     return p
 
 
-def philox_deltas(seed, iteration, dir0, count, wsize, dist=DELTA_PM1, device="cuda"):
+def counter_add(counter, inc=1):
+    """counter[0] += inc on the current stream (the device iteration counter of a captured graph)."""
+    with torch.cuda.device(counter.device):
+        _lib.check(_lib.lib().swm_counter_add(_counter_ptr(counter), int(inc), _lib.stream_ptr()))
+    return counter
+
+
+def record_nanmean(x, curve, index=None):
+    """curve[min(index[0], len-1)] = mean of the non-NaN entries of x (learning-curve entry)."""
+    x = _lib.f64(x).contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().swm_record_nanmean(_lib.ptr(x), x.numel(), _lib.ptr(curve),
+                                                 _counter_ptr(index), curve.numel(), _lib.stream_ptr()))
+    return curve
+
+
+def philox_deltas(seed, iteration, dir0, count, wsize, dist=DELTA_PM1, device="cuda", iteration_dev=None):
     """delta_k for k = dir0..dir0+count-1 as [count, wsize] -- what the kernels regenerate."""
     _lib.require_cuda()
     out = torch.empty(count, wsize, dtype=torch.float64, device=device)
-    ph = _philox(seed, iteration, dir0, dist)
+    ph = _philox(seed, iteration, dir0, dist, iteration_dev)
     with torch.cuda.device(out.device):
         _lib.check(_lib.lib().swm_philox_deltas(ctypes.byref(ph), count, wsize, _lib.ptr(out),
                                                 _lib.stream_ptr()))
@@ -244,11 +271,12 @@ def update_args(semantics, N, b):
 
 
 def ars_update(W, returns, N, *, order=None, n_order=None, divisor=0.0, ddof=0, alpha=1.0, seed=0,
-               iteration=0, dir0=0, delta_dist=DELTA_PM1, deltas=None, mask=None, sigma_out=None):
+               iteration=0, iteration_dev=None, dir0=0, delta_dist=DELTA_PM1, deltas=None, mask=None,
+               sigma_out=None):
     """In-place W += alpha * sum_{k in order[:n_order]} (r+ - r-) delta_k / (divisor * sigma_R)."""
     _lib.require_cuda()
     assert W.is_contiguous() and W.dtype == torch.float64
-    ph = _philox(seed, iteration, dir0, delta_dist)
+    ph = _philox(seed, iteration, dir0, delta_dist, iteration_dev)
     if deltas is not None:
         deltas = _lib.f64(deltas).contiguous().reshape(N, W.numel())
     n_order = N if n_order is None else int(n_order)

@@ -257,9 +257,10 @@ def test_seed_fanout_equals_sequential_agents(S, tmp_path):
     curves = fan.run(3)
     assert curves.shape == (5, 4) and np.isfinite(curves).all()
     for i, seed in enumerate(range(5)):
-        eng = S.ArsEngine(p, seed=seed, distributed=False, **kw)
+        eng = S.ArsEngine(p, seed=seed, distributed=False, curve_capacity=8, **kw)  # eager, no graph
         want = [float(torch.nanmean(eng.run_iteration()).cpu()) for _ in range(4)]
-        np.testing.assert_array_equal(curves[i], want)
+        np.testing.assert_array_equal(curves[i], eng.curve[:4].cpu().numpy())
+        np.testing.assert_allclose(curves[i], want, rtol=1e-13)
         np.testing.assert_array_equal(fan.policies()[i], eng.policy_numpy())
     assert len({tuple(c) for c in curves}) == 5  # different seeds, different curves
     ep = S.EnvParam("LeonSwimmer", n=3, H=120, l_i=1., m_i=1., h=1e-3, k=10., epsilon=0)
@@ -269,3 +270,33 @@ def test_seed_fanout_equals_sequential_agents(S, tmp_path):
     np.testing.assert_array_equal(r_graphs, curves)
     saved = list((tmp_path / "array").glob("*.npy"))
     assert len(saved) == 1 and np.array_equal(np.load(saved[0]), r_graphs)
+
+
+@pytest.mark.parametrize("mode", ["v1", "v2", "safe", "grouped"])
+def test_graph_replay_equals_eager_iterations(S, mode):
+    """The captured CUDA graph of one iteration (device-side Philox iteration counter) replays to
+    exactly the eager sequence: returns, policy, statistics and curve bit for bit, including a
+    state_dict resume in the middle."""
+    n = 10 if mode == "grouped" else 3
+    p = S.make_params(n=n, l_i=.8, m_i=1.2, k=10.2)
+    kw = dict(N=6, b=4, alpha=0.02, nu=0.05, H=60, semantics=S.ARS_TOPB, seed=9, distributed=False, curve_capacity=16)
+    if mode == "v2":
+        kw.update(v2=True, semantics=S.ARS_AGENT)
+    if mode == "grouped":
+        kw.update(v2=True, rollouts_per_direction=32, init_perturb=1e-2)
+    if mode == "safe":
+        kw.update(sim_params=S.make_params(n=n, l_i=.81, m_i=1.21, k=10.25), sim_threshold=-0.002)
+    eager, graph = S.ArsEngine(p, **kw), S.ArsEngine(p, use_graph=True, **kw)
+    for it in range(6):
+        a, b = eager.run_iteration().clone(), graph.run_iteration().clone()
+        assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)), it
+        assert torch.equal(eager.W, graph.W) and torch.equal(eager.stats, graph.stats)
+        if it == 3:  # resume both from the eager engine's checkpoint
+            sd = eager.state_dict()
+            eager.load_state_dict(sd)
+            graph.load_state_dict(sd)
+    assert graph._graph is not None and eager._graph is None
+    assert eager.iteration == graph.iteration == 6 == int(graph.iter_dev.cpu()[0])
+    ce, cg = eager.curve.cpu().numpy(), graph.curve.cpu().numpy()
+    np.testing.assert_array_equal(np.nan_to_num(ce, nan=-7.0), np.nan_to_num(cg, nan=-7.0))
+    assert np.isfinite(cg[:6]).any()
