@@ -15,7 +15,7 @@ delta tensors never move.  Nothing in an iteration synchronises with the host.
 The iteration number that keys Philox lives in device memory (`iter_dev`, advanced by
 swm_counter_add at the end of the update), so the whole iteration is a fixed sequence of launches
 with fixed arguments: `use_graph=True` captures it once into a CUDA graph and replays it (one
-launch per iteration instead of ~10; with world > 1 the NCCL all-gather is captured with it).
+launch per iteration instead of ~10; single-process engines only).
 """
 import torch
 import torch.distributed as dist
@@ -56,7 +56,9 @@ class ArsEngine:
         self.iter_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         # optional device-side learning curve: curve[j] = nanmean(returns of iteration j)
         self.curve = torch.full((int(curve_capacity),), float("nan"), **f64) if curve_capacity > 0 else None
-        self.use_graph = bool(use_graph)
+        # single-process engines only: capturing the NCCL all-gather next to eager collectives on the same
+        # communicator hung on the 2-GPU box (round 1), so sharded engines always enqueue eagerly
+        self.use_graph = bool(use_graph) and self.world == 1
         self._graph = None
         self._warm = False
         # V2 running statistics: record = [count, mean[F], M2[F]]; mean=0 / sigma=1 until the first
