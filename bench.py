@@ -23,6 +23,9 @@ sys.path.insert(0, ROOT)
 N_SEG, B_PER_GPU, H = 3, 65536, 1000
 W_REF = {3: 822, 5: 1751, 10: 5701}        # algorithmic flops per env-step
 W_REF_V2 = {3: 838, 5: 1775, 10: 5745}
+# Measured once per kernel change with ncu (profiles/r01c_summary.md), config[1] kernel, per launch:
+NCU_DRAM_BYTES_PER_LAUNCH = 1.07e6          # dram__bytes_read.sum + dram__bytes_write.sum
+NCU_EXEC_FLOPS_PER_ENV_STEP = 326.0         # executed FP64 flops per env-step: 2 per DFMA, 1 per DADD/DMUL (ncu source page)
 METRIC, UNIT = "swimmer env-steps/sec", "env-steps/s"
 WORKLOAD = "config[1]: 3-segment swimmer, 65,536 envs per GPU, fixed random actions U(-5,5), 1,000 explicit-Euler steps"
 
@@ -283,8 +286,8 @@ def run_b200(args):
                 continue
             eng = S.ArsEngine(S.make_params(n=n_), N=Ndir, b=Ndir, alpha=0.0075, nu=0.01, H=1000, v2=True,
                               semantics=S.ARS_AGENT, seed=0, device=device, rollouts_per_direction=R_,
-                              init_perturb=1e-2 if R_ > 1 else 0.0)
-            for _ in range(2 if R_ == 1 else 1):
+                              init_perturb=1e-2 if R_ > 1 else 0.0, use_graph=True)
+            for _ in range(3 if R_ == 1 else 2):  # eager warm-up, graph capture (1 GPU), replay
                 eng.run_iteration()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -302,8 +305,24 @@ def run_b200(args):
                         "iters_per_s": K2 / t_ars_s, "env_steps_per_s": K2 * steps_per_iter / t_ars_s,
                         "ms_per_iter": 1e3 * t_ars_s / K2, "iters_timed": K2,
                         "roofline_frac_fp64": (K2 * steps_per_iter / t_ars_s / world) * W_REF_V2[n_] / 1e12 / fp64_peak_tflops,
+                        "launch": "CUDA graph replay" if eng._graph is not None else "eager (NCCL exchange)",
                         "mean_return_last": float(eng.returns.mean().cpu())})
             del eng
+        if world == 1:
+            # seed fan-out (ars/experiment.py:64-72: one agent per seed): 32 agents of config[0]
+            # (n=3, V1, 8 directions, H=1000), one CUDA stream + one graph launch per agent-iteration
+            seeds, K3 = 32, 20
+            fan = S.SeedFanout(S.make_params(n=3), range(seeds), N=8, b=8, alpha=0.0075, nu=0.01, H=1000, device=device)
+            fan.run(2)
+            barrier()
+            t0 = time.perf_counter()
+            fan.run(K3, include_initial=False)
+            dt = time.perf_counter() - t0
+            ars.append({"workload": "config[0] x %d seeds: ARS V1, 3-segment swimmer, 8 directions, H=1000, one agent per "
+                                    "seed on one GPU (seed fan-out)" % seeds,
+                        "agent_iters_per_s": seeds * K3 / dt, "env_steps_per_s": seeds * K3 * 16 * 1000 / dt,
+                        "ms_per_round": 1e3 * dt / K3, "timing": "host wall clock around %d rounds incl. final sync" % K3})
+            del fan
 
     if rank == 0:
         cpu = None
@@ -324,10 +343,18 @@ def run_b200(args):
                        "l2": "flushed between steps (256 MiB write outside the timed events); inputs 1 MiB",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak_tflops, "traffic": None,
+                         "frac": achieved / fp64_peak_tflops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                                         "profiles/r01b_n3_fixed_ncu.csv): ~0 B per env-step, not HBM-bound",
                          "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 "
                                         "entry; nominal 37.2 TFLOP/s)",
                          "flops_per_env_step": W_REF[N_SEG],
+                         "executed": {"flops_per_env_step": NCU_EXEC_FLOPS_PER_ENV_STEP,
+                                      "achieved": (value / world) * NCU_EXEC_FLOPS_PER_ENV_STEP / 1e12,
+                                      "frac": (value / world) * NCU_EXEC_FLOPS_PER_ENV_STEP / 1e12 / fp64_peak_tflops,
+                                      "note": "FP64 flops the O(n) kernel really executes (ncu instruction counts) against "
+                                              "the same DFMA peak; on B200 a DFMA with three register sources issues "
+                                              "every 3 cycles, so the pipe saturates below 1.0 (profiles/r01b_summary.md)"},
                          "note": "achieved = per-GPU env-steps/s x 822 algorithmic flops/env-step of the reference's "
                                  "dense formulation (SURVEY 8d); the O(n) kernel executes fewer real flops"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B_PER_GPU * (N_SEG - 1) * 8,
