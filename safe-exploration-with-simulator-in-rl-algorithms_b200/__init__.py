@@ -5,6 +5,7 @@ Reference-shaped plugin surface (drop-in names):
     Environment                     ars/environment.py
     ARSAgent, EnvParam, ARSParam, Threshold, Database, Estimator, Experiment     ars/*.py
     Basic_ARS, Safe_ARS             safe_ars/ars.py
+    RlglueArsExperiment             rlglue/agent/SwimmerAgent.py + rlglue/experiment/SwimmerExperiment.cpp
 New batched surface: ops.step_batched / ops.rollout / ArsEngine (see include/swimmer_ars.h).
 All arithmetic runs in libswimmer_ars.so (hand-written sm_100a CUDA); there is no CPU fallback.
 """
@@ -18,6 +19,7 @@ from .environment import Environment  # noqa: F401
 from .estimator import Estimator  # noqa: F401
 from .experiment import Experiment, SeedFanout  # noqa: F401
 from .parameters import ARSParam, EnvParam, Threshold  # noqa: F401
+from .rlglue_agent import RlglueArsExperiment, read_parameters  # noqa: F401
 from .safe_ars import Basic_ARS, Safe_ARS, builtin_cost  # noqa: F401
 from .swimmer_env import SwimmerEnv  # noqa: F401
 

@@ -300,3 +300,29 @@ def test_graph_replay_equals_eager_iterations(S, mode):
     ce, cg = eager.curve.cpu().numpy(), graph.curve.cpu().numpy()
     np.testing.assert_array_equal(np.nan_to_num(ce, nan=-7.0), np.nan_to_num(cg, nan=-7.0))
     assert np.isfinite(cg[:6]).any()
+
+
+def test_rlglue_agent_experiment_matches_oracle_loop(S, O, tmp_path):
+    """RL-Glue agent semantics end to end (SwimmerAgent.py:181-241 + SwimmerExperiment.cpp:65-84):
+    clipped actions, delta ~ U[0,1), index order, first b directions, sample std, semi-implicit C++
+    dynamics from the 0.001 start state, one frozen evaluation rollout per iteration."""
+    (tmp_path / "parameters.txt").write_text(
+        "n_seg 3\ndirection 1.0 0.\nh_global 0.01\nN 4\nb 3\nH 150\nalpha 0.02\nnu 0.02\nmax_u 5.\nl_i 1.\nk 10.\nm_i 1.\n")
+    exp = S.RlglueArsExperiment.from_parameters_file(str(tmp_path / "parameters.txt"), seed=77)
+    assert (exp.N, exp.b, exp.H, exp.params.n, exp.params.h) == (4, 3, 150, 3, 0.01)
+    got = exp.run_training(4)
+    po = O.make_params(n=3, h=0.01)
+    W = np.zeros(16)
+    want = []
+    for it in range(4):
+        deltas = np.stack([O.philox_delta(77, it, k, 16, dist=1) for k in range(4)])
+        assert deltas.min() >= 0.0 and deltas.max() < 1.0
+        rets = [O.rollout(po, O.RLGLUE, 150, policy=W + s * 0.02 * deltas[k], clip=True)[0]
+                for k in range(4) for s in (+1, -1)]
+        W, _ = O.update_policy(W, deltas, np.array(rets), b=3, alpha=0.02, semantics=2)
+        want.append(O.rollout(po, O.RLGLUE, 150, policy=W, clip=True)[0])
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(exp.policy.reshape(-1), W, rtol=1e-6, atol=1e-12)
+    exp.write_results(str(tmp_path / "results.txt"))
+    lines = (tmp_path / "results.txt").read_text().splitlines()
+    assert len(lines) == 4 and lines[0].startswith("Reward for one rollout with policy at iteration 0: ")
