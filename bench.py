@@ -25,7 +25,7 @@ W_REF = {3: 822, 5: 1751, 10: 5701}        # algorithmic flops per env-step (SUR
 W_REF_V2 = {3: 838, 5: 1775, 10: 5745}
 # Measured once per kernel change with ncu (profiles/r01c_summary.md), config[1] kernel, per launch:
 NCU_DRAM_BYTES_PER_LAUNCH = 1.07e6          # dram__bytes_read.sum + dram__bytes_write.sum
-NCU_EXEC_FLOPS_PER_ENV_STEP = 326.0         # executed FP64 flops per env-step: 2 per DFMA, 1 per DADD/DMUL (ncu source page)
+NCU_EXEC_FLOPS_PER_ENV_STEP = 312.0         # executed FP64 flops per env-step: 2 per DFMA, 1 per DADD/DMUL (ncu source page)
 METRIC, UNIT = "swimmer env-steps/sec", "env-steps/s"
 WORKLOAD = "config[1]: 3-segment swimmer, 65,536 envs per GPU, fixed random actions U(-5,5), 1,000 explicit-Euler steps"
 
@@ -345,7 +345,7 @@ def run_b200(args):
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak_tflops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
-                                         "profiles/r01b_n3_fixed_ncu.csv): ~0 B per env-step, not HBM-bound",
+                                         "profiles/r01c_n3_fixed_ncu.csv): ~0 B per env-step, not HBM-bound",
                          "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 "
                                         "entry; nominal 37.2 TFLOP/s)",
                          "flops_per_env_step": W_REF[N_SEG],
