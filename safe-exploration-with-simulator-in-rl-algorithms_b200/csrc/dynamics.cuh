@@ -60,6 +60,7 @@ __device__ __forceinline__ double opaque(double x) {
   return x;
 }
 constexpr int kKeepTsTc = 7;
+constexpr int kRegLuMax = 90;  // rlglue variant: largest augmented system (doubles) factorised in registers (n <= 7)
 
 // ---------------------------------------------------------------------------------------------
 // gym variant, non-dimensional O(n) form.  With v = Gdot_i / l, g_j = 2 f_j / (m l),
@@ -325,37 +326,89 @@ __device__ __forceinline__ void rlglue_accelerations(const Phys& P, const double
     A[2 + i][S - 1] -= Bi;
   }
   // --- partially pivoted LU on [A | -const] ---
+  double z[M];
+  if constexpr (M * S <= kRegLuMax) {
+    // Small systems (n <= 7) stay in registers.  Every loop runs over a compile-time range with the
+    // triangular bounds as guards: loops whose trip count depends on the unrolled outer index were
+    // left rolled by the compiler, which put the whole system into local memory.
 #pragma unroll
-  for (int col = 0; col < M; ++col) {
-    int best = col;
-    double bv = fabs(A[col][col]);
+    for (int col = 0; col < M; ++col) {
+      int best = col;
+      double bv = fabs(A[col][col]);
 #pragma unroll
-    for (int r = col + 1; r < M; ++r) {
-      const double v = fabs(A[r][col]);
-      if (v > bv) { bv = v; best = r; }
-    }
+      for (int r = 0; r < M; ++r) {
+        if (r > col) {
+          const double v = fabs(A[r][col]);
+          if (v > bv) { bv = v; best = r; }
+        }
+      }
 #pragma unroll
-    for (int r = col + 1; r < M; ++r) {
-      if (r == best) {
+      for (int r = 0; r < M; ++r) {
+        if (r > col) {
+          const bool sw = (r == best);
 #pragma unroll
-        for (int q = col; q < S; ++q) { const double t = A[col][q]; A[col][q] = A[r][q]; A[r][q] = t; }
+          for (int q = 0; q < S; ++q) {
+            if (q >= col) {
+              const double up = A[col][q], lo = A[r][q];
+              A[col][q] = sw ? lo : up;
+              A[r][q] = sw ? up : lo;
+            }
+          }
+        }
+      }
+      const double inv = 1.0 / A[col][col];
+#pragma unroll
+      for (int r = 0; r < M; ++r) {
+        if (r > col) {
+          const double f = A[r][col] * inv;
+#pragma unroll
+          for (int q = 0; q < S; ++q)
+            if (q > col) A[r][q] = fma(-f, A[col][q], A[r][q]);
+        }
       }
     }
-    const double inv = 1.0 / A[col][col];
 #pragma unroll
-    for (int r = col + 1; r < M; ++r) {
-      const double f = A[r][col] * inv;
+    for (int r = M - 1; r >= 0; --r) {
+      double acc = -A[r][S - 1];
 #pragma unroll
-      for (int q = col + 1; q < S; ++q) A[r][q] = fma(-f, A[col][q], A[r][q]);
+      for (int q = 0; q < M; ++q)
+        if (q > r) acc = fma(-A[r][q], z[q], acc);
+      z[r] = acc / A[r][r];
     }
-  }
-  double z[M];
+  } else {
+    // Larger systems (n >= 8: more than 255 registers' worth) live in local memory; the pivot row is
+    // swapped in by predicated moves over the unrolled rows.
 #pragma unroll
-  for (int r = M - 1; r >= 0; --r) {
-    double acc = -A[r][S - 1];
+    for (int col = 0; col < M; ++col) {
+      int best = col;
+      double bv = fabs(A[col][col]);
 #pragma unroll
-    for (int q = r + 1; q < M; ++q) acc = fma(-A[r][q], z[q], acc);
-    z[r] = acc / A[r][r];
+      for (int r = col + 1; r < M; ++r) {
+        const double v = fabs(A[r][col]);
+        if (v > bv) { bv = v; best = r; }
+      }
+#pragma unroll
+      for (int r = col + 1; r < M; ++r) {
+        if (r == best) {
+#pragma unroll
+          for (int q = col; q < S; ++q) { const double t = A[col][q]; A[col][q] = A[r][q]; A[r][q] = t; }
+        }
+      }
+      const double inv = 1.0 / A[col][col];
+#pragma unroll
+      for (int r = col + 1; r < M; ++r) {
+        const double f = A[r][col] * inv;
+#pragma unroll
+        for (int q = col + 1; q < S; ++q) A[r][q] = fma(-f, A[col][q], A[r][q]);
+      }
+    }
+#pragma unroll
+    for (int r = M - 1; r >= 0; --r) {
+      double acc = -A[r][S - 1];
+#pragma unroll
+      for (int q = r + 1; q < M; ++q) acc = fma(-A[r][q], z[q], acc);
+      z[r] = acc / A[r][r];
+    }
   }
 #pragma unroll
   for (int i = 0; i < N; ++i) thdd[i] = z[2 + i];
