@@ -159,3 +159,48 @@ class SwimmerEnv:
             policies = torch.as_tensor(policies, dtype=torch.float64).to(self._dev())
         return ops.rollout(self.params(), H, variant=self.variant, actions=actions,
                            policies=policies, **kw)
+
+    # ---- host-buffer entry point (pinned memory in, pinned memory out), double-buffered ----
+    def rollout_batched_host(self, H, actions_host, returns_host, final_host=None, **kw):
+        """Fused rollout of one batch whose actions live in (pinned) HOST memory and whose results
+        are delivered into (pinned) host tensors: H2D copy -> swm_rollout -> D2H copies, all enqueued
+        on one of two internal streams so that consecutive calls overlap (the upload and download of
+        one batch hide behind the kernel of its neighbour).  Returns a CUDA event; the host tensors
+        are valid after `event.synchronize()` (or `synchronize_host()`).  The caller must not reuse
+        a host output tensor before the call that fills it has completed."""
+        dev = self._dev()
+        B = actions_host.shape[0]
+        no = 2 * self.n + 2
+        if getattr(self, "_slots", None) is None:
+            self._slots, self._slot_i = [], 0
+        if not self._slots or self._slots[0]["act"].shape[0] != B:
+            self.synchronize_host()
+            self._slots = [{"stream": torch.cuda.Stream(device=dev),
+                            "act": torch.empty(B, self.n - 1, dtype=torch.float64, device=dev),
+                            "out": {"returns": torch.empty(B, dtype=torch.float64, device=dev),
+                                    "final_state": torch.empty(B, no, dtype=torch.float64, device=dev)},
+                            "event": None} for _ in range(2)]
+        slot = self._slots[self._slot_i]
+        self._slot_i ^= 1
+        st = slot["stream"]
+        st.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(st):
+            slot["act"].copy_(actions_host, non_blocking=True)
+            res = ops.rollout(self.params(), H, variant=self.variant, actions=slot["act"],
+                              want_final=final_host is not None,
+                              out=slot["out"] if final_host is not None else {"returns": slot["out"]["returns"]},
+                              **kw)
+            returns_host.copy_(res.returns, non_blocking=True)
+            if final_host is not None:
+                final_host.copy_(res.final_state, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        slot["event"] = ev
+        return ev
+
+    def synchronize_host(self):
+        """Waits for every outstanding `rollout_batched_host` call; the current stream also waits."""
+        for slot in getattr(self, "_slots", None) or []:
+            if slot["event"] is not None:
+                torch.cuda.current_stream(self._dev()).wait_event(slot["event"])
+                slot["event"].synchronize()

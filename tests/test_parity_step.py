@@ -127,3 +127,25 @@ def test_empty_and_bad_arguments(S):
         S.make_params(n=1)
     with pytest.raises(ValueError):
         S.ops.step_batched(p, torch.zeros(4, 8, device="cuda"), torch.zeros(4, 2, device="cuda"))  # fp32
+
+
+def test_rollout_batched_host_double_buffered(S):
+    """Host-buffer entry point: pinned actions in, pinned results out, consecutive calls overlap on two
+    streams; results equal the device-tensor path bit for bit, for every call of a back-to-back run."""
+    env = S.SwimmerEnv(n=3)
+    rng = np.random.default_rng(5)
+    B, H = 4096, 100
+    acts = [torch.as_tensor(rng.uniform(-5, 5, (B, 2))).pin_memory() for _ in range(5)]
+    rets = [torch.empty(B, dtype=torch.float64).pin_memory() for _ in range(5)]
+    fins = [torch.empty(B, 8, dtype=torch.float64).pin_memory() for _ in range(5)]
+    evs = [env.rollout_batched_host(H, acts[i], rets[i], fins[i]) for i in range(5)]
+    env.synchronize_host()
+    assert all(e.query() for e in evs)
+    for i in range(5):
+        ref = env.rollout_batched(H, actions=acts[i], want_final=True)
+        assert torch.equal(rets[i], ref.returns.cpu()) and torch.equal(fins[i], ref.final_state.cpu())
+    # a different batch size re-creates the slots; returns-only variant
+    small = torch.as_tensor(rng.uniform(-5, 5, (64, 2))).pin_memory()
+    r = torch.empty(64, dtype=torch.float64).pin_memory()
+    env.rollout_batched_host(H, small, r).synchronize()
+    assert torch.equal(r, env.rollout_batched(H, actions=small).returns.cpu())
