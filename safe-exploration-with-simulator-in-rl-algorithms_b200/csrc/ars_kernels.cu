@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include "../../include/swimmer_ars.h"
+#include "errors.cuh"
 #include "philox.cuh"
 
 namespace swm {
@@ -279,7 +280,7 @@ record_nanmean_kernel(const double* __restrict__ x, int n, double* __restrict__ 
 
 using namespace swm;
 
-#define SWM_CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? SWM_OK : SWM_ERR_CUDA)
+#define SWM_CHECK_LAUNCH() swm::check_launch()
 
 extern "C" int swm_ars_topb(const double* returns, const int32_t* mask, int N, int32_t* order,
                             void* stream) {

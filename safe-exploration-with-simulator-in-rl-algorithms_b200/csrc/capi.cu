@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include "errors.cuh"
 #include "launch.cuh"
 
 using namespace swm;
@@ -25,6 +26,16 @@ int note_launch(int rc) {
   }
   return rc;
 }
+
+}  // namespace
+
+int swm::check_launch() {
+  const cudaError_t e = cudaGetLastError();  // reads and clears
+  if (e == cudaSuccess) return SWM_OK;
+  return cuda_fail(e);
+}
+
+namespace {
 
 bool params_ok(const swm_params_t* p) {
   return p && p->n >= SWM_MIN_SEGMENTS && p->n <= SWM_MAX_SEGMENTS && p->l_i > 0.0 && p->m_i > 0.0;

@@ -27,13 +27,15 @@ static int launch_rollout_one(const RolloutArgs& a, cudaStream_t st) {
   if (WMODE == W_SMEM_GROUP) smem = sizeof(double) * WS * (kRolloutBlock / 32);
   if (STATS && (2 * N + 2) > kRegStatsMaxObs) smem += sizeof(double) * 2 * (2 * N + 2) * kRolloutBlock;
   auto kern = rollout_kernel<N, VARIANT, WMODE, NORM, STATS, SCREEN>;
-  if (smem > 48 * 1024) {
+  // dynamic + static shared memory (s_mu, s_piv, the moment reduction scratch: < 2 KB) above the default
+  // 48 KB limit needs the opt-in attribute
+  if (smem + 2048 > 48 * 1024) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return SWM_ERR_CUDA;
   }
   const long long blocks = (a.B + kRolloutBlock - 1) / kRolloutBlock;
   kern<<<(unsigned)blocks, kRolloutBlock, smem, st>>>(a);
-  return cudaGetLastError() == cudaSuccess ? SWM_OK : SWM_ERR_CUDA;
+  return cudaPeekAtLastError() == cudaSuccess ? SWM_OK : SWM_ERR_CUDA;  // capi.cu note_launch reads + clears it
 }
 
 template <int N, int WMODE>
@@ -79,7 +81,7 @@ int launch_step_n(const Phys& P, int variant, bool acc_only, const double* state
     if (acc_only) step_kernel<N, 1, true><<<blocks, kStepBlock, 0, st>>>(P, state_in, action, out, reward, B);
     else step_kernel<N, 1, false><<<blocks, kStepBlock, 0, st>>>(P, state_in, action, out, reward, B);
   }
-  return cudaGetLastError() == cudaSuccess ? SWM_OK : SWM_ERR_CUDA;
+  return cudaPeekAtLastError() == cudaSuccess ? SWM_OK : SWM_ERR_CUDA;  // capi.cu note_launch reads + clears it
 }
 
 template int launch_step_n<SWM_INSTANTIATE_N>(const Phys&, int, bool, const double*, const double*,

@@ -240,3 +240,37 @@ def test_tracked_trig_tiers_match_oracle(S, O, n):
     assert np.isnan(r2[7])
     keep = np.arange(B) != 7
     np.testing.assert_array_equal(r2[keep], got_r[keep])
+
+
+@pytest.mark.parametrize("n,R", [(5, 1), (7, 1), (8, 1), (10, 1), (7, 32), (10, 64)])
+def test_v2_rollouts_and_moments_every_storage_mode(S, O, n, R):
+    """V2 rollouts + moments for every combination of policy storage (per-thread / per-warp shared
+    memory) and moment storage (registers up to n = 7, shared memory above), including the
+    shared-memory sizes right at the 48 KB opt-in limit (n = 7)."""
+    H, D = 80, 3
+    ps, po = S.make_params(n=n), O.make_params(n=n)
+    no, ws = 2 * n + 2, (n - 1) * (2 * n + 2)
+    rng = np.random.default_rng(100 + n + R)
+    W = rng.uniform(-1, 1, ws) * 0.1
+    mean, var = rng.normal(size=no) * 0.05, rng.uniform(.5, 2, no)
+    pivot = S.ops.reset_state(n)
+    init = rand_states(rng, n, R, scale=0.3) if R > 1 else None
+    B = 2 * D * R
+    res = S.ops.rollout(ps, H, B=B, base_policy=_cuda(W), nu=0.05, seed=12, iteration=1, rollouts_per_policy=R,
+                        mean=_cuda(mean), inv_sigma=_cuda(var ** -0.5), stats_pivot=pivot,
+                        init_state=None if init is None else _cuda(init))
+    got = res.returns.cpu().numpy().reshape(D, 2, R)
+    rec = S.ops.stats_finalize(res.stats_partial, res.samples, pivot).cpu().numpy()
+    trajs = []
+    for k in range(D):
+        d = O.philox_delta(12, 1, k, ws)
+        for j, sign in enumerate((+1, -1)):
+            for r in range(R):
+                ret, _, tr = O.rollout(po, O.GYM, H, policy=W + sign * 0.05 * d, mean=mean, inv_sigma=var ** -0.5,
+                                       init_state=None if init is None else init[r], want_traj=True)
+                assert abs(got[k, j, r] - ret) < RET_TOL * max(1e-3, abs(ret))
+                trajs.append(tr)
+    m, v = O.mean_var(np.concatenate(trajs))
+    assert rec[0] == B * H
+    np.testing.assert_allclose(rec[1:1 + no], m, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(rec[1 + no:] / (rec[0] - 1), v, rtol=1e-8)
