@@ -10,10 +10,10 @@ import torch
 import swimmer_ars_b200 as S
 
 
-def main():
+def main(ns=(2, 3, 4, 5, 6, 7, 8, 9, 10)):
     rng = np.random.default_rng(0)
     H = 70  # crosses the step-63 re-evaluation
-    for n in (2, 3, 5, 7, 8, 10):
+    for n in ns:
         p = S.make_params(n=n)
         no, na, ws = 2 * n + 2, n - 1, (n - 1) * (2 * n + 2)
         B = 70  # ragged second block
@@ -30,7 +30,9 @@ def main():
         for R, Bp in ((1, 70), (3, 2 * 7 * 3), (32, 2 * 2 * 32), (64, 2 * 1 * 64)):
             r = S.ops.rollout(p, H, B=Bp, base_policy=W, nu=0.05, seed=3, rollouts_per_policy=R,
                               init_perturb=1e-2 if R > 1 else 0.0, mean=mean, inv_sigma=inv, stats_pivot=piv)
-            S.ops.stats_finalize(r.stats_partial, r.samples, piv)
+            rec = S.ops.stats_finalize(r.stats_partial, r.samples, piv)
+            assert bool(torch.isfinite(r.returns).all()) and bool(torch.isfinite(rec).all())
+            assert float(rec[0]) == Bp * H
             S.ops.rollout(p, H, B=Bp, base_policy=W, nu=0.05, seed=3, rollouts_per_policy=R, want_final=True)
             S.ops.rollout(p, H, B=Bp, variant=S.RLGLUE, base_policy=W, nu=0.05, seed=3, rollouts_per_policy=R,
                           clip_actions=True, delta_dist=S.DELTA_01)
