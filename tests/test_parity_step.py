@@ -149,3 +149,53 @@ def test_rollout_batched_host_double_buffered(S):
     r = torch.empty(64, dtype=torch.float64).pin_memory()
     env.rollout_batched_host(H, small, r).synchronize()
     assert torch.equal(r, env.rollout_batched(H, actions=small).returns.cpu())
+
+
+def test_rlglue_env_plugin_symbols_end_to_end(S, O, tmp_path):
+    """The five RL-Glue environment symbols (SwimmerEnvironment.h:38-42) driven the way the RL-Glue codec
+    drives them: parameters from a flat parameters.txt, start state 0.001, steps against the oracle's
+    restatement of SwimmerEnvironment.cpp, save/load state, callee-owned static storage."""
+    import ctypes
+
+    class RL(ctypes.Structure):
+        _fields_ = [("numInts", ctypes.c_uint), ("numDoubles", ctypes.c_uint), ("numChars", ctypes.c_uint),
+                    ("intArray", ctypes.POINTER(ctypes.c_int)), ("doubleArray", ctypes.POINTER(ctypes.c_double)),
+                    ("charArray", ctypes.c_char_p)]
+
+    class ROT(ctypes.Structure):
+        _fields_ = [("reward", ctypes.c_double), ("observation", ctypes.POINTER(RL)), ("terminal", ctypes.c_int)]
+
+    L = S._lib.lib()
+    L.env_init.restype = ctypes.c_char_p
+    L.env_start.restype = ctypes.POINTER(RL)
+    L.env_step.restype = ctypes.POINTER(ROT)
+    L.env_step.argtypes = [ctypes.POINTER(RL)]
+    L.env_message.restype = ctypes.c_char_p
+    L.env_message.argtypes = [ctypes.c_char_p]
+    pf = tmp_path / "parameters.txt"
+    pf.write_text("n_seg 3\ndirection 1.0 0.\nh_global 0.01\nN 1\nb 1\nH 1000\nalpha 0.02\nnu 0.02\nmax_u 5.\nl_i 1.\nk 10.\nm_i 1.\n")
+    msg = L.env_message(("set parameters " + str(pf)).encode()).decode()
+    assert "n_seg=3" in msg and "h_global=0.01" in msg
+    spec = L.env_init().decode()
+    assert spec.startswith("VERSION RL-Glue-3.0") and "OBSERVATIONS DOUBLES" in spec and "ACTIONS DOUBLES" in spec
+    assert L.env_message(b"what is your name?").decode().lower().startswith("my name is")
+    obs = L.env_start().contents
+    assert obs.numDoubles == 8 and [obs.doubleArray[i] for i in range(8)] == [0.001] * 8
+    act_vals = (ctypes.c_double * 2)(1.5, -2.0)
+    act = RL(0, 2, 0, None, act_vals, None)
+    po = O.make_params(n=3, h=0.01)
+    st = np.full(8, 0.001)
+    for t in range(12):
+        r = L.env_step(ctypes.byref(act)).contents
+        st, want_rew = O.step(po, O.RLGLUE, st, [1.5, -2.0])
+        got = np.array([r.observation.contents.doubleArray[i] for i in range(8)])
+        assert rel_err(got, st) < 1e-11 and abs(r.reward - want_rew) < 1e-11 and r.terminal == 0
+        if t == 4:
+            assert L.env_message(b"save state").decode().startswith("saved_observation")
+            saved = st.copy()
+    assert L.env_message(b"load state").decode().startswith("this_observation")
+    r = L.env_step(ctypes.byref(act)).contents
+    want, _ = O.step(po, O.RLGLUE, saved, [1.5, -2.0])
+    assert rel_err(np.array([r.observation.contents.doubleArray[i] for i in range(8)]), want) < 1e-11
+    assert "does not respond" in L.env_message(b"anything else").decode()
+    L.env_cleanup()
