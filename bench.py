@@ -116,7 +116,7 @@ def run_reference(args):
     if cpp:
         line["ref_cpp_rlglue_1core"] = {"value": cpp, "unit": UNIT, "kind": "reference",
                                         "note": "unmodified rlglue/environment/SwimmerEnvironment.cpp updateState, n=3"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -394,14 +394,32 @@ def run_b200(args):
         }
         if ars:
             line["ars"] = ars
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints there while the run
+    is in progress (e.g. NCCL's version banner) has been redirected to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
