@@ -90,7 +90,9 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    envs = cpu_sample_size(threads, 4.0)
+    # bounded sample per step: the whole run (K timed + W warm-up steps) stays near two minutes
+    per_step_s = min(4.0, max(0.25, 100.0 / max(1, args.steps + args.warmup)))
+    envs = cpu_sample_size(threads, per_step_s)
     for _ in range(args.warmup):
         cpu_fixed_action_rate(max(threads, envs // 8), H, threads)
     t_tot, done = 0.0, 0
