@@ -164,13 +164,15 @@ class ARSAgent:
             if host_deltas is None:
                 host_deltas = ops.philox_deltas(eng.seed, eng.iteration - 1, 0, ap.N, eng.ws,
                                                 eng.delta_dist, eng.device).cpu().numpy()
-            for i in np.nonzero(ok)[0]:
-                d = np.asarray(host_deltas[i]).reshape(pre_W.shape)
-                for s, pol in ((0, pre_W + ap.nu * d), (1, pre_W - ap.nu * d)):
-                    states = traj[:, 2 * i + s, :].tolist()
-                    if self.keep_states and not ap.V1:
-                        self.saved_states += states
-                    self.database.add_trajectory(states, pol)
+            kept_dirs = np.nonzero(ok)[0]
+            if len(kept_dirs):
+                d = np.stack([np.asarray(host_deltas[i]).reshape(pre_W.shape) for i in kept_dirs])
+                pols = np.stack([pre_W + ap.nu * d, pre_W - ap.nu * d], axis=1).reshape((-1,) + pre_W.shape)
+                cols = np.stack([2 * kept_dirs, 2 * kept_dirs + 1], axis=1).reshape(-1)  # [+0, -0, +1, -1, ...]
+                self.database.extend_from_rollout(traj[:, cols, :], pols)
+                if self.keep_states and not ap.V1:
+                    for c in cols:
+                        self.saved_states += traj[:, c, :].tolist()
         return kept
 
     @property
