@@ -274,3 +274,22 @@ def test_v2_rollouts_and_moments_every_storage_mode(S, O, n, R):
     assert rec[0] == B * H
     np.testing.assert_allclose(rec[1:1 + no], m, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(rec[1 + no:] / (rec[0] - 1), v, rtol=1e-8)
+
+
+@pytest.mark.parametrize("n", [3, 5, 10])
+def test_one_step_rollout_equals_batched_step(S, O, n):
+    """H = 1: the fused kernel's step (tracked trig, folded constants) and the batched single-step kernel
+    (fresh sincos) agree to round-off, and both with the oracle within the single-step tolerance 1e-12."""
+    ps, po = S.make_params(n=n), O.make_params(n=n)
+    rng = np.random.default_rng(70 + n)
+    B = 200
+    st = rand_states(rng, n, B)
+    ac = rng.uniform(-5, 5, (B, n - 1))
+    roll = S.ops.rollout(ps, 1, actions=_cuda(ac), init_state=_cuda(st), want_final=True)
+    nxt, rew = S.ops.step_batched(ps, _cuda(st), _cuda(ac))
+    want, want_r = O.step_batch(po, O.GYM, st, ac)
+    assert rel_err(roll.final_state.cpu().numpy(), want) < 1e-12
+    assert rel_err(nxt.cpu().numpy(), want) < 1e-12
+    assert rel_err(roll.final_state.cpu().numpy(), nxt.cpu().numpy()) < 1e-13
+    np.testing.assert_allclose(roll.returns.cpu().numpy(), want_r, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(rew.cpu().numpy(), want_r, rtol=1e-11, atol=1e-13)
