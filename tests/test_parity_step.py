@@ -199,3 +199,29 @@ def test_rlglue_env_plugin_symbols_end_to_end(S, O, tmp_path):
     assert rel_err(np.array([r.observation.contents.doubleArray[i] for i in range(8)]), want) < 1e-11
     assert "does not respond" in L.env_message(b"anything else").decode()
     L.env_cleanup()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_physical_parameters_step_and_rollout(S, O, seed):
+    """The kernels work in a non-dimensional form with constants folded on the host: random segment
+    length / mass / viscosity (including k = 0) / step / direction must still match the oracle's
+    dimensional dense formulation, single step at 1e-12 and a 150-step policy rollout at 1e-6."""
+    rng = np.random.default_rng(900 + seed)
+    n = int(rng.integers(2, 11))
+    kw = dict(n=n, l_i=float(rng.uniform(0.3, 3.0)), m_i=float(rng.uniform(0.2, 5.0)),
+              k=float(0.0 if seed == 0 else rng.uniform(0.5, 50.0)), h=float(10 ** rng.uniform(-4, -2.3)),
+              direction=tuple(rng.normal(size=2)))
+    ps, po = S.make_params(**kw), O.make_params(**kw)
+    B = 64
+    st = rand_states(rng, n, B, scale=1.0)
+    ac = rng.uniform(-5, 5, (B, n - 1))
+    got, got_r = S.ops.step_batched(ps, torch.as_tensor(st).cuda(), torch.as_tensor(ac).cuda())
+    want, want_r = O.step_batch(po, O.GYM, st, ac)
+    assert rel_err(got.cpu().numpy(), want) < 1e-12, kw
+    np.testing.assert_allclose(got_r.cpu().numpy(), want_r, rtol=1e-10, atol=1e-12)
+    Ws = rng.uniform(-1, 1, (8, n - 1, 2 * n + 2)) * 0.2
+    res = S.ops.rollout(ps, 150, policies=torch.as_tensor(Ws).cuda(), want_final=True)
+    for q in range(8):
+        ret, fin, _ = O.rollout(po, O.GYM, 150, policy=Ws[q])
+        assert abs(float(res.returns[q].cpu()) - ret) < 1e-6 * max(1e-3, abs(ret)), (kw, q)
+        assert rel_err(res.final_state[q].cpu().numpy(), fin) < 1e-8, (kw, q)
