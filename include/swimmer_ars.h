@@ -159,6 +159,15 @@ SWM_API int swm_step_batched(const swm_params_t* params, int variant, const doub
                      const double* action, double* state_out, double* reward, int64_t B,
                      void* stream);
 
+/* Batched single step with SEVERAL models in one launch: environment e uses params[e / envs_per_model]
+ * (host array of n_models <= SWM_MAX_MODELS_PER_STEP structs with the same n).  This is the shape of the
+ * parameter-estimation objective Estimator.I (ars/estimator.py:36-62): every CMA-ES candidate
+ * (m_i, l_i, k) predicts the same recorded states one step ahead.  gym variant only. */
+#define SWM_MAX_MODELS_PER_STEP 24
+SWM_API int swm_step_batched_models(const swm_params_t* params, int n_models, int64_t envs_per_model,
+                                    const double* state_in, const double* action, double* state_out,
+                                    double* reward, void* stream);
+
 /* Accelerations only (compute_accelerations, remy_swimmer_env.py:95-114 / cpp:139-226):
  * acc[B, n+2] = [Gdd_x, Gdd_y, thdd_1..thdd_n]. */
 SWM_API int swm_accelerations_batched(const swm_params_t* params, int variant, const double* state,

@@ -19,6 +19,7 @@ DELTA_PM1, DELTA_01 = 0, 1
 ARS_AGENT, ARS_TOPB, ARS_RLGLUE = 0, 1, 2
 MIN_SEGMENTS, MAX_SEGMENTS = 2, 10
 ABI_VERSION = 2  # include/swimmer_ars.h SWM_ABI_VERSION
+MAX_MODELS_PER_STEP = 24  # SWM_MAX_MODELS_PER_STEP
 
 _dp = ctypes.c_void_p
 
@@ -89,6 +90,7 @@ def lib():
     L.swm_device_info.argtypes = [ctypes.POINTER(c_int)] * 3
     L.swm_step_batched.argtypes = [pp, c_int, _dp, _dp, _dp, _dp, i64, _dp]
     L.swm_accelerations_batched.argtypes = [pp, c_int, _dp, _dp, _dp, i64, _dp]
+    L.swm_step_batched_models.argtypes = [pp, c_int, i64, _dp, _dp, _dp, _dp, _dp]
     L.swm_rollout.argtypes = [pp, ctypes.POINTER(SwmRollout), _dp]
     L.swm_rollout_stats_blocks.argtypes = [pp, ctypes.POINTER(SwmRollout)]
     L.swm_rollout_stats_blocks.restype = i64

@@ -123,6 +123,25 @@ extern "C" int swm_step_batched(const swm_params_t* params, int variant, const d
   return step_common(params, variant, false, state_in, action, state_out, reward, B, stream);
 }
 
+extern "C" int swm_step_batched_models(const swm_params_t* params, int n_models, int64_t envs_per_model,
+                                       const double* state_in, const double* action, double* state_out,
+                                       double* reward, void* stream) {
+  if (!params || n_models < 1 || n_models > SWM_MAX_MODELS_PER_STEP || envs_per_model < 0) return SWM_ERR_BAD_ARG;
+  PhysSet set;
+  for (int i = 0; i < n_models; ++i) {
+    if (!params_ok(&params[i]) || params[i].n != params[0].n) return SWM_ERR_BAD_ARG;
+    set.p[i] = make_phys(&params[i]);
+  }
+  for (int i = n_models; i < SWM_MAX_MODELS_PER_STEP; ++i) set.p[i] = set.p[0];
+  const long long B = (long long)n_models * envs_per_model;
+  if (B == 0) return SWM_OK;
+  if (!state_in || !action || !state_out) return SWM_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(K) launch_step_models_n<K>(set, (long long)envs_per_model, state_in, action, state_out, reward, B, st)
+  SWM_DISPATCH_N(params[0].n, CALL)
+#undef CALL
+}
+
 extern "C" int swm_accelerations_batched(const swm_params_t* params, int variant,
                                          const double* state, const double* action, double* acc,
                                          int64_t B, void* stream) {

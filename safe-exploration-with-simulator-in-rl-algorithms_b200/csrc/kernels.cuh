@@ -110,6 +110,37 @@ step_kernel(Phys P, const double* __restrict__ state_in, const double* __restric
   if (reward) reward[e] = r;
 }
 
+// Several models in one launch (Estimator.I over a CMA-ES generation): the models travel in the
+// kernel-argument constant bank, env e uses model e / envs_per_model.
+struct PhysSet {
+  Phys p[SWM_MAX_MODELS_PER_STEP];
+};
+
+template <int N>
+__global__ void __launch_bounds__(kStepBlock)
+step_models_kernel(const __grid_constant__ PhysSet set, long long envs_per_model,
+                   const double* __restrict__ state_in, const double* __restrict__ action,
+                   double* __restrict__ state_out, double* __restrict__ reward, long long B) {
+  constexpr int NO = 2 * N + 2, NA = N - 1;
+  const long long e = (long long)blockIdx.x * kStepBlock + threadIdx.x;
+  if (e >= B) return;
+  const Phys& P = set.p[e / envs_per_model];
+  const double2* sp = reinterpret_cast<const double2*>(state_in + e * NO);
+  double gdx, gdy, th[N], thd[N], u[NA > 0 ? NA : 1];
+  const double2 g = sp[0];
+  gdx = g.x; gdy = g.y;
+#pragma unroll
+  for (int i = 0; i < N; ++i) { const double2 v = sp[1 + i]; th[i] = v.x; thd[i] = v.y; }
+#pragma unroll
+  for (int a = 0; a < NA; ++a) u[a] = action[e * NA + a];
+  const double r = swimmer_step<N, 0>(P, gdx, gdy, th, thd, u);
+  double2* op = reinterpret_cast<double2*>(state_out + e * NO);
+  op[0] = make_double2(gdx, gdy);
+#pragma unroll
+  for (int i = 0; i < N; ++i) op[1 + i] = make_double2(th[i], thd[i]);
+  if (reward) reward[e] = r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // fused rollout
 // ---------------------------------------------------------------------------------------------

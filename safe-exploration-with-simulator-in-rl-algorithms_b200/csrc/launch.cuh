@@ -16,6 +16,9 @@ template <int N> int launch_step_n(const Phys& P, int variant, bool acc_only, co
                                    const double* action, double* out, double* reward, long long B,
                                    cudaStream_t st);
 template <int N> int launch_rollout_n(const RolloutArgs& a, const RolloutFlags& f, cudaStream_t st);
+template <int N> int launch_step_models_n(const PhysSet& set, long long envs_per_model, const double* state_in,
+                                          const double* action, double* out, double* reward, long long B,
+                                          cudaStream_t st);
 
 #ifdef SWM_INSTANTIATE_N
 
@@ -84,6 +87,16 @@ int launch_step_n(const Phys& P, int variant, bool acc_only, const double* state
   return cudaPeekAtLastError() == cudaSuccess ? SWM_OK : SWM_ERR_CUDA;  // capi.cu note_launch reads + clears it
 }
 
+template <int N>
+int launch_step_models_n(const PhysSet& set, long long envs_per_model, const double* state_in,
+                         const double* action, double* out, double* reward, long long B, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((B + kStepBlock - 1) / kStepBlock);
+  step_models_kernel<N><<<blocks, kStepBlock, 0, st>>>(set, envs_per_model, state_in, action, out, reward, B);
+  return cudaPeekAtLastError() == cudaSuccess ? SWM_OK : SWM_ERR_CUDA;
+}
+
+template int launch_step_models_n<SWM_INSTANTIATE_N>(const PhysSet&, long long, const double*, const double*,
+                                                     double*, double*, long long, cudaStream_t);
 template int launch_step_n<SWM_INSTANTIATE_N>(const Phys&, int, bool, const double*, const double*,
                                               double*, double*, long long, cudaStream_t);
 template int launch_rollout_n<SWM_INSTANTIATE_N>(const RolloutArgs&, const RolloutFlags&, cudaStream_t);

@@ -57,8 +57,21 @@ class Estimator:
         return float(total.cpu())
 
     def I_population(self, xs):
-        """Objective for a whole CMA-ES generation (list of candidates) -> list of floats."""
-        return [self.I(x) for x in xs]
+        """Objective for a whole CMA-ES generation (list of candidates) -> list of floats: for every
+        recorded trajectory ONE launch steps all candidates' models from the same states
+        (swm_step_batched_models); the actions W_k s_t do not depend on the candidate."""
+        cands = [self.convert_to_env_param(x) for x in xs]
+        plist = [_lib.make_params(n=p.n, l_i=p.l_i, m_i=p.m_i, k=p.k, h=p.h) for p in cands]
+        M = len(plist)
+        total = torch.zeros(M, dtype=torch.float64, device=self.device)
+        for k in self.subset:
+            traj, policy = self._traj(int(k))
+            s = traj[:-1].contiguous()
+            act = ops.policy_actions(plist[0], s, policy.reshape(1, -1), rollouts_per_policy=s.shape[0])
+            nxt, _ = ops.step_batched_models(plist, s.unsqueeze(0).expand(M, -1, -1).contiguous(),
+                                             act.unsqueeze(0).expand(M, -1, -1).contiguous())
+            total = total + torch.linalg.norm(nxt - traj[1:].unsqueeze(0), dim=2).sum(dim=1)
+        return total.cpu().tolist()
 
     def estimate_real_env_param(self):
         """CMA-ES over I (ars/estimator.py:89-110); needs the third-party `cma` package."""

@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import (ARS_AGENT, ARS_RLGLUE, ARS_TOPB, DELTA_01, DELTA_PM1, GYM, POLICY_DELTAS,
                    POLICY_EXPLICIT, POLICY_FIXED_ACTION, POLICY_PHILOX, RLGLUE)
 
-__all__ = ["step_batched", "accelerations_batched", "rollout", "RolloutResult", "philox_deltas",
+__all__ = ["step_batched", "step_batched_models", "accelerations_batched", "rollout", "RolloutResult", "philox_deltas",
            "ars_topb", "ars_update", "counter_add", "record_nanmean", "stats_finalize", "stats_merge", "reduce_returns", "screen_mask", "policy_actions", "update_args",
            "fp64_probe", "obs_dim", "act_dim", "policy_size", "reset_state"]
 
@@ -60,6 +60,29 @@ def step_batched(params, states, actions, variant=GYM, out=None, want_reward=Tru
         _lib.check(_lib.lib().swm_step_batched(ctypes.byref(params), variant, _lib.ptr(states),
                                                _lib.ptr(actions), _lib.ptr(out), _lib.ptr(rew), B,
                                                _lib.stream_ptr()))
+    return out, rew
+
+
+def step_batched_models(params_list, states, actions, out=None, want_reward=False):
+    """states[M, T, 2n+2], actions[M, T, n-1]: model m (params_list[m]) steps its T environments, all
+    in one launch (swm_step_batched_models; at most MAX_MODELS_PER_STEP models per launch, more are
+    chunked).  -> (next_states[M, T, 2n+2], rewards[M, T] or None)."""
+    _lib.require_cuda()
+    M = len(params_list)
+    n = params_list[0].n
+    T = states.shape[1]
+    _lib.f64(states, (M, T, obs_dim(n)))
+    _lib.f64(actions, (M, T, act_dim(n)))
+    states, actions = states.contiguous(), actions.contiguous()
+    out = torch.empty_like(states) if out is None else out
+    rew = torch.empty(M, T, dtype=torch.float64, device=states.device) if want_reward else None
+    with torch.cuda.device(states.device):
+        for lo in range(0, M, _lib.MAX_MODELS_PER_STEP):
+            hi = min(M, lo + _lib.MAX_MODELS_PER_STEP)
+            arr = (_lib.SwmParams * (hi - lo))(*params_list[lo:hi])
+            _lib.check(_lib.lib().swm_step_batched_models(
+                arr, hi - lo, T, _lib.ptr(states[lo:hi]), _lib.ptr(actions[lo:hi]), _lib.ptr(out[lo:hi]),
+                _lib.ptr(rew[lo:hi]) if rew is not None else None, _lib.stream_ptr()))
     return out, rew
 
 

@@ -246,6 +246,13 @@ def test_estimator_objective(S, O):
         nxt, _ = O.step(p2, 0, traj[t], W @ traj[t])
         want += np.linalg.norm(nxt - traj[t + 1])
     assert abs(est.I(x) - want) < 1e-9 * want
+    # a whole CMA-ES generation in one launch per trajectory (swm_step_batched_models): same numbers as
+    # one candidate at a time, also beyond the 24 models one launch carries
+    xs = [[1.0, 1.0, 10.0], x] + [list(np.array(x) * (1 + 0.01 * i)) for i in range(1, 28)]
+    pop = est.I_population(xs)
+    assert len(pop) == 29 and pop[0] < 1e-12 and abs(pop[1] - want) < 1e-9 * want
+    for i in (2, 17, 23, 24, 28):
+        assert abs(pop[i] - est.I(xs[i])) <= 1e-12 * max(1.0, pop[i])
 
 
 def test_seed_fanout_equals_sequential_agents(S, tmp_path):
