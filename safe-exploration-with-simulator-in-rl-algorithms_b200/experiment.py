@@ -8,7 +8,8 @@ exchange between them.
 
 `SeedFanout` is the batched engine-level entry point; `Experiment` keeps the reference's
 constructor / `plot(n_seed, agent_param)` call shape and `.npy` output, without the matplotlib
-figures (plotting is out of scope).
+figures (plotting is out of scope).  The scripts ars/plot_graph.py and
+ars/safe_exploration.py run on it with only their imports changed (examples/).
 """
 import os
 
@@ -91,12 +92,26 @@ class Experiment:
         self.guess_param, self.approx_error, self.sim_thresh = guess_param, approx_error, sim_thresh
         self.device = device
 
-    def plot(self, n_seed, agent_param, plot_mean=True):
+    def plot(self, n_seed, agent_param, plot_mean=True, delta_source=None):
+        """`delta_source`: "philox" = seed fan-out on CUDA streams (default for plain training), "numpy" = one
+        `ARSAgent` per seed consuming numpy's global stream exactly like the reference (same seed, same
+        curve).  Safe exploration and trajectory recording (`save_data_path`) always go through
+        `ARSAgent`, which owns the database / estimator / simulator-threshold logic of
+        ars_agent.py:37-71."""
         p = self.real_env_param
-        if agent_param.safe:
-            raise NotImplementedError(
-                "Experiment.plot fans out unconstrained agents; for safe exploration build ARSAgent "
-                "per seed (it owns the estimator / database logic of ars_agent.py:37-71)")
+        via_agents = (agent_param.safe or self.save_data_path is not None or delta_source == "numpy")
+        if via_agents:
+            from .ars_agent import ARSAgent
+            curves, last = [], None
+            for i in range(n_seed):  # experiment.py:64-72, one actor per seed
+                last = ARSAgent(p, agent_param, seed=i, data_path=self.data_path, guess_param=self.guess_param,
+                                approx_error=self.approx_error, sim_thresh=self.sim_thresh,
+                                delta_source=delta_source or "numpy", device=self.device)
+                curves.append(last.runTraining(save_data_path=self.save_data_path,
+                                               save_policy_path=self.save_policy_path))
+            r_graphs = np.array(curves)
+            self._save_array(agent_param, r_graphs)
+            return r_graphs
         if agent_param.initial_w == "Zero":
             W0 = None
         else:
@@ -108,13 +123,20 @@ class Experiment:
         r_graphs = fan.run(agent_param.n_iter)
         if self.save_policy_path is not None:
             np.save(self.save_policy_path, fan.policies()[-1])  # the reference's actors overwrite one file
-        if self.results_path is not None:
-            ars = (f"{agent_param.name}, ARS_{'V1' if agent_param.V1 else 'V2'}"
-                   f"{'-t' if agent_param.b < agent_param.N else ''}, n_directions={agent_param.N}, "
-                   f"deltas_used={agent_param.b}, step_size={agent_param.alpha}, delta_std={agent_param.nu}")
-            env = (f"{p.name}, n_segments={p.n}, m_i={round(p.m_i, 2)}, l_i={round(p.l_i, 2)}, "
-                   f"epsilon={round(p.epsilon, 4)}, deltaT={p.h}")
-            d = os.path.join(self.results_path, "array")
-            os.makedirs(d, exist_ok=True)
-            np.save(os.path.join(d, f"{env.replace(', ', '-')}-{ars.replace(', ', '-')}"), r_graphs)
+        self._save_array(agent_param, r_graphs)
         return r_graphs
+
+    def _save_array(self, agent_param, r_graphs):
+        """`np.save` of the curves under results_path/array/ with the reference's file name
+        (experiment.py:90-93)."""
+        if self.results_path is None:
+            return
+        p = self.real_env_param
+        ars = (f"{agent_param.name}, ARS_{'V1' if agent_param.V1 else 'V2'}"
+               f"{'-t' if agent_param.b < agent_param.N else ''}, n_directions={agent_param.N}, "
+               f"deltas_used={agent_param.b}, step_size={agent_param.alpha}, delta_std={agent_param.nu}")
+        env = (f"{p.name}, n_segments={p.n}, m_i={round(p.m_i, 2)}, l_i={round(p.l_i, 2)}, "
+               f"epsilon={round(p.epsilon, 4)}, deltaT={p.h}")
+        d = os.path.join(self.results_path, "array")
+        os.makedirs(d, exist_ok=True)
+        np.save(os.path.join(d, f"{env.replace(', ', '-')}-{ars.replace(', ', '-')}"), r_graphs)

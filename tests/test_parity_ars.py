@@ -333,3 +333,28 @@ def test_rlglue_agent_experiment_matches_oracle_loop(S, O, tmp_path):
     exp.write_results(str(tmp_path / "results.txt"))
     lines = (tmp_path / "results.txt").read_text().splitlines()
     assert len(lines) == 4 and lines[0].startswith("Reward for one rollout with policy at iteration 0: ")
+
+
+def test_reference_scripts_run_with_changed_imports(tmp_path):
+    """examples/plot_graph.py and examples/safe_exploration.py are the reference's ars/plot_graph.py and
+    ars/safe_exploration.py with only the imports changed; a miniature run of both must complete and
+    respect the reward constraint semantics (a real rollout is only made when both simulated returns of
+    its direction exceed the simulator threshold)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "plot_graph.py"), "--n_seed", "3",
+                          "--n_iter", "4", "--results_path", str(tmp_path) + "/"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    saved = list((tmp_path / "array").glob("*.npy"))
+    assert len(saved) == 1 and np.load(saved[0]).shape == (3, 5)
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "safe_exploration.py"), "--quick",
+                          "--data_dir", str(tmp_path / "data")], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Safety threshold" in out.stdout and "Using approximated estimation" in out.stdout
+    res = np.load(next((tmp_path / "data").glob("epsilon_sim_threshold_*.npz")))
+    assert res["min_return"].shape == (2,) and np.isfinite(res["safety_threshold"])
+    db = np.load(tmp_path / "data" / "real_world_2.npz")
+    assert db["trajectories"].shape[1:] == (200, 8) and db["policies"].shape[1:] == (2, 8)
