@@ -358,3 +358,13 @@ def test_reference_scripts_run_with_changed_imports(tmp_path):
     assert res["min_return"].shape == (2,) and np.isfinite(res["safety_threshold"])
     db = np.load(tmp_path / "data" / "real_world_2.npz")
     assert db["trajectories"].shape[1:] == (200, 8) and db["policies"].shape[1:] == (2, 8)
+    # safe_ars/experiment.py: per-step state-constraint screening keeps every real step under the threshold
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "safe_ars_experiment.py"), "--n_iter", "6",
+                          "--n_rollout", "150", "--n_seeds", "2", "--thresh", "1.5", "--nu", "0.3",
+                          "--path", str(tmp_path / "safe_ars")], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = np.load(next((tmp_path / "safe_ars").glob("*.npz")))
+    assert res["safe_returns"].shape == (2, 6) and res["safe_costs"].shape == (2, 2 * 6 * 150)
+    # the simulator screens every step at thresh - 1 = 0.5: the real cost never reaches the threshold 1.5,
+    # while the unconstrained agent is free to exceed it
+    assert 0.0 < res["safe_costs"].max() <= 1.5
