@@ -6,7 +6,7 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 SRC=$ROOT/safe-exploration-with-simulator-in-rl-algorithms_b200/csrc
 mkdir -p /tmp/fastpath
 for n in "$@"; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DSWM_ANALYZE_TIER=${TIER:-0} -c $SRC/rollout_n$n.cu -o /tmp/fastpath/n$n.o &
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DSWM_ANALYZE_TIER=${TIER:-0} ${EXTRA_DEFS} -c $SRC/rollout_n$n.cu -o /tmp/fastpath/n$n.o &
 done
 wait
 for n in "$@"; do
