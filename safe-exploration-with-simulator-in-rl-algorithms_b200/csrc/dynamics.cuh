@@ -193,6 +193,7 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
 // kernel re-evaluates (s, c) exactly from th every 64th step, so truncation never accumulates over
 // more than 63 steps.
 constexpr double kRotateShort = 0.03125, kRotateLong = 0.125;
+constexpr int kRotateShortHi = 0x3FA00000, kRotateLongHi = 0x3FC00000;  // high words of 1/32 and 1/8
 __device__ __forceinline__ void small_sincos_base(double d, double& z, double& sn, double& cm1) {
   z = d * d;
   const double ps = fma(z, 8.3333333333333332e-03, -1.6666666666666666e-01);  // 1/5!, -1/3!
@@ -484,11 +485,15 @@ __device__ __forceinline__ void gym_step_tracked(const Phys& P, double& gdx, dou
   gdx = fma(P.h_gdd_c, psx, gdx);
   gdy = fma(P.h_gdd_c, psy, gdy);
   double d[N];
-  double dmax = 0.0;
+  // Tier selection on the integer pipe: for non-negative doubles the high word orders like the value, so
+  // max_i |d_i| is taken as the maximum of the sign-stripped high words (NaN / Inf have the largest ones
+  // and fall through to sincos).  Thresholds are powers of two (low word 0): hi <= hi(threshold) admits
+  // |d| < threshold * (1 + 2^-20), which the polynomial bounds cover.
+  int dmax_hi = 0;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     d[i] = P.h * thd[i];
-    dmax = fmax(dmax, fabs(d[i]));
+    dmax_hi = max(dmax_hi, __double2hiint(d[i]) & 0x7fffffff);
     th[i] = fma(P.h, thd[i], th[i]);
     thd[i] = fma(P.h, thdd[i], thd[i]);
   }
@@ -506,11 +511,11 @@ __device__ __forceinline__ void gym_step_tracked(const Phys& P, double& gdx, dou
   for (int i = 0; i < N; ++i) rotate_by(sn[i], cm1[i], s[i], c[i]);
   return;
 #endif
-  if (!(dmax <= kRotateShort)) {
+  if (dmax_hi > kRotateShortHi) {
 #pragma unroll
     for (int i = 0; i < N; ++i) small_sincos_tail(d[i], z[i], sn[i], cm1[i]);
   }
-  if (resync || !(dmax <= kRotateLong)) {
+  if (resync || dmax_hi > kRotateLongHi) {
 #pragma unroll
     for (int i = 0; i < N; ++i) sincos(th[i], &s[i], &c[i]);
   } else {

@@ -146,14 +146,16 @@ step_models_kernel(const __grid_constant__ PhysSet set, long long envs_per_model
 // ---------------------------------------------------------------------------------------------
 template <int N>
 __device__ __forceinline__ double cost_max_abs_thd(const double (&thd)[N]) {
-  // safe_ars/experiment.py:44  np.max(|obs[3+2i]|); NaN propagates like np.max
-  double cst = 0.0;
+  // safe_ars/experiment.py:44  np.max(|obs[3+2i]|); NaN propagates like np.max.  The sign-stripped bit
+  // patterns of doubles order like their magnitudes (NaN above everything), so the maximum is taken on
+  // the integer pipe and the FP64 unit only sees the final comparison with the threshold.
+  long long m = 0;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const double a = fabs(thd[i]);
-    cst = (a > cst || a != a) ? a : cst;
+    const long long b = __double_as_longlong(thd[i]) & 0x7fffffffffffffffLL;
+    m = b > m ? b : m;
   }
-  return cst;
+  return __longlong_as_double(m);
 }
 
 // LINEAR: 0 fixed actions, 1 linear policy.  NORM: ARS V2 normalisation.  STATS: accumulate
