@@ -143,6 +143,12 @@ typedef struct {
                                    sums of (x-pivot) and (x-pivot)^2 over all visited states */
   const double* stats_pivot;    /* [2n+2], required with stats_partial */
   swm_screen_t screen;
+  int32_t accumulate_returns;   /* 1: returns[e] += this launch's sum instead of overwriting it.  Lets a caller
+                                   cut one rollout into time-chunks (final_state of one launch = init_state of the
+                                   next) and sub-batches on several streams, which removes the quantisation of
+                                   mid-size batches over SM sub-partitions; chunk lengths that are multiples of 64
+                                   keep the visited states bit-identical to the single launch. */
+  int32_t _pad2;
 } swm_rollout_t;
 
 SWM_API int swm_abi_version(void);

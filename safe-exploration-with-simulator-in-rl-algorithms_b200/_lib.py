@@ -50,7 +50,7 @@ class SwmRollout(ctypes.Structure):
                 ("inv_sigma", _dp), ("init_state", _dp), ("init_state_count", ctypes.c_int64),
                 ("init_perturb", ctypes.c_double), ("returns", _dp), ("final_state", _dp),
                 ("trajectory", _dp), ("stats_partial", _dp), ("stats_pivot", _dp),
-                ("screen", SwmScreen)]
+                ("screen", SwmScreen), ("accumulate_returns", ctypes.c_int32), ("_pad2", ctypes.c_int32)]
 
 
 class SwimmerLibError(RuntimeError):

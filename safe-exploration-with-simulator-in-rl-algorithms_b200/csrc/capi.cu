@@ -226,6 +226,7 @@ extern "C" int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg,
   a.real_thresh = cfg->screen.real_thresh;
   a.violations = cfg->screen.violations;
   a.frozen_at = cfg->screen.frozen_at;
+  a.accumulate = cfg->accumulate_returns;
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(K) launch_rollout_n<K>(a, f, st)
   SWM_DISPATCH_N(params->n, CALL)

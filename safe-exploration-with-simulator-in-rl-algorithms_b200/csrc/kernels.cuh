@@ -61,6 +61,7 @@ struct RolloutArgs {
   double sim_thresh, real_thresh;
   int* violations;
   int* frozen_at;
+  int accumulate;  // returns[e] += instead of =
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -228,7 +229,6 @@ rollout_kernel(const RolloutArgs a) {
     const double* dmem = from_mem ? a.deltas + (q >> 1) * WS : nullptr;
     const double sgn_nu = (q & 1) ? -a.nu : a.nu;
     const unsigned int dir = a.dir0 + (unsigned int)(q >> 1);
-    const bool writer = (WMODE != W_SMEM_GROUP) || ((tid & 31) == 0);
     auto make_pair = [&](int j, double& w0, double& w1) {
       w0 = base[j];
       w1 = (j + 1 < WS) ? base[j + 1] : 0.0;
@@ -257,18 +257,22 @@ rollout_kernel(const RolloutArgs a) {
         Wr[j] = w0;
         if (j + 1 < WS) Wr[j + 1] = w1;
       }
-    } else if (writer) {
+    } else if (WMODE == W_SMEM_GROUP) {
+      // the 32 lanes of the warp share the Philox calls of their common policy
+#pragma unroll 1
+      for (int j = 2 * (tid & 31); j < WS; j += 64) {
+        double w0, w1;
+        make_pair(j, w0, w1);
+        sW[(j % NO) * NA + j / NO] = w0;  // [obs][action] (see the policy product in the step loop)
+        if (j + 1 < WS) sW[((j + 1) % NO) * NA + (j + 1) / NO] = w1;
+      }
+    } else {
 #pragma unroll 1
       for (int j = 0; j < WS; j += 2) {
         double w0, w1;
         make_pair(j, w0, w1);
-        if (WMODE == W_SMEM_GROUP) {  // [obs][action] (see the policy product in the step loop)
-          sW[(j % NO) * NA + j / NO] = w0;
-          if (j + 1 < WS) sW[((j + 1) % NO) * NA + (j + 1) / NO] = w1;
-        } else {
-          sW[j * wstride] = w0;
-          if (j + 1 < WS) sW[(j + 1) * wstride] = w1;
-        }
+        sW[j * wstride] = w0;
+        if (j + 1 < WS) sW[(j + 1) * wstride] = w1;
       }
     }
     if (WMODE == W_SMEM_GROUP) __syncwarp();
@@ -413,7 +417,7 @@ rollout_kernel(const RolloutArgs a) {
 
   if (VARIANT == 0) ret += fma(sgx, a.real.dirx, sgy * a.real.diry);
   if (active) {
-    a.returns[e] = ret;
+    a.returns[e] = a.accumulate ? a.returns[e] + ret : ret;
     if (a.final_state) {
       double2* o = reinterpret_cast<double2*>(a.final_state + e * NO);
       o[0] = make_double2(gdx, gdy);

@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import (ARS_AGENT, ARS_RLGLUE, ARS_TOPB, DELTA_01, DELTA_PM1, GYM, POLICY_DELTAS,
                    POLICY_EXPLICIT, POLICY_FIXED_ACTION, POLICY_PHILOX, RLGLUE)
 
-__all__ = ["step_batched", "step_batched_models", "accelerations_batched", "rollout", "RolloutResult", "philox_deltas",
+__all__ = ["step_batched", "step_batched_models", "accelerations_batched", "rollout", "RolloutResult", "ChunkedRollout", "philox_deltas",
            "ars_topb", "ars_update", "counter_add", "record_nanmean", "stats_finalize", "stats_merge", "reduce_returns", "screen_mask", "policy_actions", "update_args",
            "fp64_probe", "obs_dim", "act_dim", "policy_size", "reset_state"]
 
@@ -115,7 +115,8 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
             deltas=None, dir_mask=None, init_perturb=0.0,
             seed=0, iteration=0, iteration_dev=None, dir0=0, delta_dist=DELTA_PM1, rollouts_per_policy=1, mean=None,
             inv_sigma=None, clip_actions=False, init_state=None, want_final=False,
-            want_trajectory=False, stats_pivot=None, screen=None, out=None, device=None):
+            want_trajectory=False, stats_pivot=None, screen=None, out=None, device=None,
+            accumulate_returns=False):
     """One fused H-step rollout of B environments (swm_rollout).
 
     Exactly one of
@@ -171,6 +172,7 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
     cfg.variant, cfg.H, cfg.B = variant, int(H), int(B)
     cfg.rollouts_per_policy = int(rollouts_per_policy)
     cfg.clip_actions = int(bool(clip_actions))
+    cfg.accumulate_returns = int(bool(accumulate_returns))
     cfg.nu = float(nu)
     cfg.init_perturb = float(init_perturb)
     cfg.philox.seed, cfg.philox.iteration = int(seed) & (2 ** 64 - 1), int(iteration)
@@ -225,6 +227,101 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().swm_rollout(ctypes.byref(params), ctypes.byref(cfg), _lib.stream_ptr()))
     return res
+
+
+class ChunkedRollout:
+    """One rollout call scheduled as `n_sub` sub-batches x time-chunks of `chunk` steps on `n_sub` CUDA
+    streams (swm_rollout launches chained through final_state -> init_state, returns accumulated on the
+    device).  Why: one thread owns one environment for all H steps, so a mid-size batch is quantised over
+    SM sub-partitions (65,536 three-segment envs = 3.46 warps each, the busiest holds 4) or over waves of
+    resident CTAs; short launches from several streams let the hardware refill whatever finishes first
+    (+17 % on BASELINE config[1]).  `chunk` must be a multiple of 64: the kernel re-evaluates its tracked
+    sines/cosines exactly every 64th step, so every visited state is bit-identical to the single launch
+    (returns differ by the rounding of K partial sums).  Not available with screening or trajectory
+    output.  All tensors handed in are captured by reference: call `run()` repeatedly (also inside a CUDA
+    graph capture) after updating them in place."""
+
+    def __init__(self, params, H, *, B, n_sub=8, chunk=128, variant=GYM, actions=None, base_policy=None,
+                 policies=None, rollouts_per_policy=1, stats_pivot=None, want_final=True, device=None, **kw):
+        _lib.require_cuda()
+        if chunk % 64 != 0 or chunk < 64:
+            raise ValueError("chunk must be a positive multiple of 64")
+        if kw.get("screen") is not None or kw.get("want_trajectory"):
+            raise ValueError("chunked rollouts do not support screening or trajectory output")
+        n = params.n
+        self.params, self.H, self.B, self.variant, self.kw = params, int(H), int(B), variant, kw
+        self.R = int(rollouts_per_policy)
+        self.actions, self.base_policy, self.policies = actions, base_policy, policies
+        src = actions if actions is not None else (base_policy if base_policy is not None else policies)
+        self.device = torch.device(device) if device is not None else src.device
+        # sub-batches are whole policy groups (2R envs per direction for perturbed policies)
+        unit = self.R * (2 if base_policy is not None else 1)
+        groups = self.B // unit
+        n_sub = max(1, min(int(n_sub), groups))
+        cuts = [unit * ((groups * i) // n_sub) for i in range(n_sub + 1)]
+        self.subs = [(cuts[i], cuts[i + 1]) for i in range(n_sub) if cuts[i + 1] > cuts[i]]
+        self.lens = [min(chunk, self.H - t) for t in range(0, self.H, chunk)]
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.returns = torch.zeros(self.B, **f64)
+        self.state = torch.empty(self.B, obs_dim(n), **f64)
+        self.want_final = want_final
+        self.stats_pivot = stats_pivot
+        self.stats_partial, self._rows = None, None
+        if stats_pivot is not None:
+            blocks = [(hi - lo + 63) // 64 for lo, hi in self.subs]  # kRolloutBlock
+            self._rows, r = [], 0
+            for _ in self.lens:
+                row = []
+                for b in blocks:
+                    row.append((r, r + b))
+                    r += b
+                self._rows.append(row)
+            self.stats_partial = torch.zeros(r, 2, obs_dim(n), **f64)
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.subs]
+        self.launches = len(self.subs) * len(self.lens)
+
+    def run(self, dir0=0, **overrides):
+        """Enqueues all launches (current stream forks into the sub-batch streams and joins again) and
+        returns a RolloutResult with returns[B], final_state[B, 2n+2], stats_partial / samples."""
+        kw = dict(self.kw)
+        kw.update(overrides)
+        init_perturb = kw.pop("init_perturb", 0.0)
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+        unit = self.R * (2 if self.base_policy is not None else 1)
+        for c, L in enumerate(self.lens):
+            for i, ((lo, hi), st) in enumerate(zip(self.subs, self.streams)):
+                out = {"returns": self.returns[lo:hi], "final_state": self.state[lo:hi]}
+                if self.stats_partial is not None:
+                    r0, r1 = self._rows[c][i]
+                    out["stats_partial"] = self.stats_partial[r0:r1]
+                src = {}
+                if self.actions is not None:
+                    src["actions"] = self.actions[lo:hi]
+                elif self.base_policy is not None:
+                    src.update(base_policy=self.base_policy, B=hi - lo, dir0=dir0 + lo // unit)
+                    if kw.get("deltas") is not None:
+                        src["deltas"] = kw["deltas"][lo // unit:hi // unit]
+                    if kw.get("dir_mask") is not None:
+                        src["dir_mask"] = kw["dir_mask"][lo // unit:hi // unit]
+                else:
+                    src["policies"] = self.policies.reshape(self.B // self.R, -1)[lo // self.R:hi // self.R]
+                call = {k: v for k, v in kw.items() if k not in ("deltas", "dir_mask")}
+                with torch.cuda.stream(st):
+                    rollout(self.params, L, variant=self.variant, rollouts_per_policy=self.R,
+                            init_state=None if c == 0 else self.state[lo:hi],
+                            init_perturb=init_perturb if c == 0 else 0.0, want_final=True,
+                            stats_pivot=self.stats_pivot, accumulate_returns=c > 0, out=out, **src, **call)
+        for st in self.streams:
+            cur.wait_stream(st)
+        res = RolloutResult()
+        res.returns, res.final_state = self.returns, self.state
+        res.stats_partial = self.stats_partial
+        if self.stats_partial is not None:
+            res.stats_blocks = self.stats_partial.shape[0]
+            res.samples = float(self.B) * float(self.H)
+        return res
 
 
 def _counter_ptr(t):

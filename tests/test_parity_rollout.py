@@ -293,3 +293,56 @@ def test_one_step_rollout_equals_batched_step(S, O, n):
     assert rel_err(roll.final_state.cpu().numpy(), nxt.cpu().numpy()) < 1e-13
     np.testing.assert_allclose(roll.returns.cpu().numpy(), want_r, rtol=1e-11, atol=1e-13)
     np.testing.assert_allclose(rew.cpu().numpy(), want_r, rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("case", ["fixed_n3", "philox_v2_n5", "grouped_n10", "explicit_n7"])
+def test_chunked_rollout_equals_single_launch(S, case):
+    """ops.ChunkedRollout (sub-batches x 64-step-aligned time chunks on several streams, state chained through
+    final_state -> init_state, returns accumulated on the device): every final state bit-identical to the
+    single launch, returns equal up to the rounding of the partial sums, V2 moments equal to 1e-12."""
+    rng = np.random.default_rng(31)
+    if case == "fixed_n3":
+        n, B, H = 3, 5000, 300
+        p = S.make_params(n=n)
+        kw = dict(actions=_cuda(rng.uniform(-5, 5, (B, n - 1))))
+        extra = {}
+    elif case == "philox_v2_n5":
+        n, B, H = 5, 2 * 150, 200
+        p = S.make_params(n=n)
+        no = 2 * n + 2
+        kw = dict(base_policy=_cuda(rng.uniform(-1, 1, (n - 1) * no) * 0.1), stats_pivot=S.ops.reset_state(n))
+        extra = dict(nu=0.05, seed=4, iteration=3, mean=_cuda(rng.normal(size=no) * 0.05),
+                     inv_sigma=_cuda(rng.uniform(.5, 2, no)))
+    elif case == "grouped_n10":
+        n, R, D, H = 10, 32, 6, 150
+        B = 2 * D * R
+        p = S.make_params(n=n)
+        no = 2 * n + 2
+        kw = dict(base_policy=_cuda(rng.uniform(-1, 1, (n - 1) * no) * 0.05), rollouts_per_policy=R,
+                  stats_pivot=S.ops.reset_state(n))
+        extra = dict(nu=0.05, seed=9, iteration=1, init_perturb=1e-2, mean=_cuda(np.zeros(no)),
+                     inv_sigma=_cuda(np.ones(no)))
+    else:
+        n, B, H = 7, 96, 130
+        p = S.make_params(n=n)
+        kw = dict(policies=_cuda(rng.uniform(-1, 1, (B, n - 1, 2 * n + 2)) * 0.1))
+        extra = {}
+    single_kw = dict(kw)
+    single_kw.update(extra)
+    if "actions" not in kw and "policies" not in kw:
+        single_kw["B"] = B
+    ref = S.ops.rollout(p, H, want_final=True, dir0=5 if "base_policy" in kw else 0, **single_kw)
+    for n_sub, chunk in ((1, 64), (3, 64), (4, 128)):
+        plan = S.ops.ChunkedRollout(p, H, B=B, n_sub=n_sub, chunk=chunk, **kw, **extra)
+        for _ in range(2):  # re-running reuses the buffers
+            got = plan.run(dir0=5 if "base_policy" in kw else 0)
+            torch.cuda.synchronize()
+            assert torch.equal(got.final_state, ref.final_state), (case, n_sub, chunk)
+            np.testing.assert_allclose(got.returns.cpu().numpy(), ref.returns.cpu().numpy(), rtol=1e-12, atol=1e-13)
+            if ref.stats_partial is not None:
+                piv = kw["stats_pivot"]
+                a = S.ops.stats_finalize(got.stats_partial, got.samples, piv).cpu().numpy()
+                b = S.ops.stats_finalize(ref.stats_partial, ref.samples, piv).cpu().numpy()
+                np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-13)
+    with pytest.raises(ValueError):
+        S.ops.ChunkedRollout(p, H, B=B, chunk=100, **kw, **extra)
