@@ -29,7 +29,7 @@ class ArsEngine:
                  rollouts_per_direction=1, seed=0, variant=GYM, delta_dist=DELTA_PM1,
                  clip_actions=False, init_perturb=0.0, initial_policy=None, group=None,
                  distributed=None, device=None, sim_params=None, sim_threshold=None,
-                 step_screen=None, use_graph=False, curve_capacity=0):
+                 step_screen=None, use_graph=False, curve_capacity=0, rollout_chunks=None):
         _lib.require_cuda()
         self.params, self.N, self.b, self.alpha, self.nu, self.H = params, int(N), int(b), alpha, nu, int(H)
         self.v2, self.semantics, self.R = bool(v2), semantics, int(rollouts_per_direction)
@@ -90,9 +90,24 @@ class ArsEngine:
             self.mask = torch.ones(self.N, dtype=torch.int32, device=self.device)
             self.sim_returns = torch.zeros(Bl, **f64)
         self.last = None
+        # optional (n_sub, chunk): schedule the real rollouts as sub-batches x time-chunks on several streams
+        # (ops.ChunkedRollout) -- pays off when 2 N R / world environments are a mid-size batch
+        self._chunked = None
+        if rollout_chunks is not None and step_screen is None:
+            n_sub, chunk = rollout_chunks
+            kw = dict(nu=self.nu, seed=self.seed, iteration=0, iteration_dev=self.iter_dev,
+                      delta_dist=self.delta_dist, clip_actions=self.clip, init_perturb=self.init_perturb)
+            if self.v2:
+                kw.update(mean=self.mean, inv_sigma=self.inv_sigma)
+            self._chunked = ops.ChunkedRollout(
+                params, self.H, B=Bl, n_sub=n_sub, chunk=chunk, variant=self.variant, base_policy=self.W,
+                rollouts_per_policy=self.R, stats_pivot=self.pivot if self.v2 else None, device=self.device, **kw)
 
     # -------------------------------------------------------------------------------------------
     def _rollouts(self, params, out, deltas_local, dir_mask, want_stats, want_trajectory, screen):
+        if (self._chunked is not None and params is self.params and not want_trajectory and screen is None
+                and want_stats == self.v2):
+            return self._chunked.run(dir0=self.dir0, deltas=deltas_local, dir_mask=dir_mask)
         return ops.rollout(
             params, self.H, B=self.B_local, variant=self.variant, base_policy=self.W, nu=self.nu,
             deltas=deltas_local, dir_mask=dir_mask, init_perturb=self.init_perturb, seed=self.seed,
@@ -138,7 +153,7 @@ class ArsEngine:
         res = self._rollouts(self.params, self._out, deltas_local, dir_mask, self.v2, want_trajectory,
                              self.step_screen)
         self.last = res
-        if res.stats_partial is not None:
+        if res.stats_partial is not None and res.stats_partial is not getattr(self._chunked, "stats_partial", None):
             self._out["stats_partial"] = res.stats_partial  # reuse: iterations allocate nothing
         rec = self._record
         if R == 1:

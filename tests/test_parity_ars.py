@@ -368,3 +368,30 @@ def test_reference_scripts_run_with_changed_imports(tmp_path):
     # the simulator screens every step at thresh - 1 = 0.5: the real cost never reaches the threshold 1.5,
     # while the unconstrained agent is free to exceed it
     assert 0.0 < res["safe_costs"].max() <= 1.5
+
+
+@pytest.mark.parametrize("mode", ["v2", "grouped", "safe"])
+def test_engine_with_chunked_rollouts_matches_plain_engine(S, mode):
+    """ArsEngine(rollout_chunks=(n_sub, chunk)) schedules the real rollouts as sub-batches x time-chunks on
+    several streams: same returns (rounding of the partial sums), same policy and statistics within 1e-10
+    after three iterations, also under graph replay and with a screening mask."""
+    n = 10 if mode == "grouped" else 5
+    p = S.make_params(n=n)
+    kw = dict(N=12, b=6, alpha=0.02, nu=0.05, H=200, v2=True, semantics=S.ARS_TOPB, seed=2, distributed=False)
+    if mode == "grouped":
+        kw.update(rollouts_per_direction=32, init_perturb=1e-2)
+    if mode == "safe":
+        kw.update(sim_params=S.make_params(n=n, l_i=1.01, m_i=0.99, k=10.1), sim_threshold=-0.001)
+    plain = S.ArsEngine(p, **kw)
+    chunked = S.ArsEngine(p, rollout_chunks=(3, 64), **kw)
+    graphed = S.ArsEngine(p, rollout_chunks=(3, 64), use_graph=True, **kw)
+    for it in range(3):
+        a, b, c = plain.run_iteration().clone(), chunked.run_iteration().clone(), graphed.run_iteration().clone()
+        assert torch.equal(torch.isnan(a), torch.isnan(b))
+        np.testing.assert_allclose(torch.nan_to_num(b).cpu().numpy(), torch.nan_to_num(a).cpu().numpy(),
+                                   rtol=1e-9, atol=1e-12)
+        assert torch.equal(torch.nan_to_num(b), torch.nan_to_num(c))  # graph replay = eager, bit for bit
+        np.testing.assert_allclose(chunked.W.cpu().numpy(), plain.W.cpu().numpy(), rtol=1e-8, atol=1e-11)
+        np.testing.assert_allclose(chunked.inv_sigma.cpu().numpy(), plain.inv_sigma.cpu().numpy(), rtol=1e-9)
+        assert torch.equal(chunked.W, graphed.W) and torch.equal(chunked.stats, graphed.stats)
+    assert graphed._graph is not None
