@@ -205,7 +205,7 @@ def run_b200(args):
     # (ops.ChunkedRollout: swm_rollout launches chained through final_state -> init_state, replayed from one
     # CUDA graph).  Every final state is bit-identical to the single launch; short launches from several
     # streams remove the quantisation of 65,536 envs over the SM sub-partitions (3.46 warps each).
-    plan = S.ops.ChunkedRollout(params, H, B=B_PER_GPU, n_sub=16, chunk=64, actions=actions)
+    plan = S.SwimmerEnv(n=N_SEG, device=device).rollout_plan(H, n_sub=16, chunk=64, actions=actions)
     plan.run()
     torch.cuda.synchronize()
     step_graph = torch.cuda.CUDAGraph()

@@ -160,6 +160,19 @@ class SwimmerEnv:
         return ops.rollout(self.params(), H, variant=self.variant, actions=actions,
                            policies=policies, **kw)
 
+    def rollout_plan(self, H, *, n_sub=16, chunk=64, actions=None, policies=None, **kw):
+        """A reusable schedule of one fused rollout as `n_sub` sub-batches x `chunk`-step launches on several
+        streams (ops.ChunkedRollout): `plan.run()` enqueues it (capturable in a CUDA graph) and returns the same
+        results as `rollout_batched` -- final states bit-identical -- while filling the SMs better when the
+        batch is a fractional number of warps per SM sub-partition (65,536 envs on a B200: +18 %).  The
+        tensors are captured by reference: update them in place between runs."""
+        src = actions if actions is not None else policies
+        src = torch.as_tensor(src, dtype=torch.float64).to(self._dev())
+        B = src.shape[0] * (kw.get("rollouts_per_policy", 1) if policies is not None else 1)
+        return ops.ChunkedRollout(self.params(), H, B=B, n_sub=n_sub, chunk=chunk, variant=self.variant,
+                                  actions=src if actions is not None else None,
+                                  policies=src if policies is not None else None, **kw)
+
     # ---- host-buffer entry point (pinned memory in, pinned memory out), double-buffered ----
     def rollout_batched_host(self, H, actions_host, returns_host, final_host=None, **kw):
         """Fused rollout of one batch whose actions live in (pinned) HOST memory and whose results

@@ -225,3 +225,14 @@ def test_random_physical_parameters_step_and_rollout(S, O, seed):
         ret, fin, _ = O.rollout(po, O.GYM, 150, policy=Ws[q])
         assert abs(float(res.returns[q].cpu()) - ret) < 1e-6 * max(1e-3, abs(ret)), (kw, q)
         assert rel_err(res.final_state[q].cpu().numpy(), fin) < 1e-8, (kw, q)
+
+
+def test_rollout_plan_through_the_env_surface(S):
+    """SwimmerEnv.rollout_plan = the chunked schedule behind the drop-in class; same results as rollout_batched."""
+    env = S.SwimmerEnv(n=3)
+    ac = torch.as_tensor(np.random.default_rng(2).uniform(-5, 5, (3000, 2))).cuda()
+    plan = env.rollout_plan(200, n_sub=4, chunk=64, actions=ac)
+    got = plan.run()
+    ref = env.rollout_batched(200, actions=ac, want_final=True)
+    assert torch.equal(got.final_state, ref.final_state) and plan.launches == 4 * 4
+    np.testing.assert_allclose(got.returns.cpu().numpy(), ref.returns.cpu().numpy(), rtol=1e-12, atol=1e-13)
