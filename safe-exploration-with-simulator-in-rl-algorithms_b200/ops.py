@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import (ARS_AGENT, ARS_RLGLUE, ARS_TOPB, DELTA_01, DELTA_PM1, GYM, POLICY_DELTAS,
                    POLICY_EXPLICIT, POLICY_FIXED_ACTION, POLICY_PHILOX, RLGLUE)
 
-__all__ = ["step_batched", "step_batched_models", "accelerations_batched", "rollout", "RolloutResult", "ChunkedRollout", "philox_deltas",
+__all__ = ["step_batched", "step_batched_models", "accelerations_batched", "rollout", "RolloutResult", "ChunkedRollout", "plan_chunks", "philox_deltas",
            "ars_topb", "ars_update", "counter_add", "record_nanmean", "stats_finalize", "stats_merge", "reduce_returns", "screen_mask", "policy_actions", "update_args",
            "fp64_probe", "obs_dim", "act_dim", "policy_size", "reset_state"]
 
@@ -229,6 +229,22 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
     return res
 
 
+def plan_chunks(B, unit, n_sub, H, chunk):
+    """Host-side partition behind ChunkedRollout: B environments in whole groups of `unit` (the envs that
+    share a direction) are cut into at most `n_sub` contiguous sub-batches, H steps into chunks of `chunk`
+    (a multiple of 64; the last one may be shorter).  -> ([(lo, hi), ...], [len, ...])."""
+    if chunk % 64 != 0 or chunk < 64:
+        raise ValueError("chunk must be a positive multiple of 64")
+    if B % unit != 0:
+        raise ValueError("B=%d is not a whole number of groups of %d environments" % (B, unit))
+    groups = B // unit
+    n_sub = max(1, min(int(n_sub), groups))
+    cuts = [unit * ((groups * i) // n_sub) for i in range(n_sub + 1)]
+    subs = [(cuts[i], cuts[i + 1]) for i in range(n_sub) if cuts[i + 1] > cuts[i]]
+    lens = [min(chunk, H - t) for t in range(0, H, chunk)]
+    return subs, lens
+
+
 class ChunkedRollout:
     """One rollout call scheduled as `n_sub` sub-batches x time-chunks of `chunk` steps on `n_sub` CUDA
     streams (swm_rollout launches chained through final_state -> init_state, returns accumulated on the
@@ -244,8 +260,6 @@ class ChunkedRollout:
     def __init__(self, params, H, *, B, n_sub=8, chunk=128, variant=GYM, actions=None, base_policy=None,
                  policies=None, rollouts_per_policy=1, stats_pivot=None, want_final=True, device=None, **kw):
         _lib.require_cuda()
-        if chunk % 64 != 0 or chunk < 64:
-            raise ValueError("chunk must be a positive multiple of 64")
         if kw.get("screen") is not None or kw.get("want_trajectory"):
             raise ValueError("chunked rollouts do not support screening or trajectory output")
         n = params.n
@@ -256,11 +270,7 @@ class ChunkedRollout:
         self.device = torch.device(device) if device is not None else src.device
         # sub-batches are whole policy groups (2R envs per direction for perturbed policies)
         unit = self.R * (2 if base_policy is not None else 1)
-        groups = self.B // unit
-        n_sub = max(1, min(int(n_sub), groups))
-        cuts = [unit * ((groups * i) // n_sub) for i in range(n_sub + 1)]
-        self.subs = [(cuts[i], cuts[i + 1]) for i in range(n_sub) if cuts[i + 1] > cuts[i]]
-        self.lens = [min(chunk, self.H - t) for t in range(0, self.H, chunk)]
+        self.subs, self.lens = plan_chunks(self.B, unit, n_sub, self.H, chunk)
         f64 = dict(dtype=torch.float64, device=self.device)
         self.returns = torch.zeros(self.B, **f64)
         self.state = torch.empty(self.B, obs_dim(n), **f64)

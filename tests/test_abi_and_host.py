@@ -143,3 +143,24 @@ def test_sharding_and_packed_allgather_gloo(S):
     assert D.shard_directions(1024, 3, 8) == (384, 512)
     with pytest.raises(ValueError):
         D.shard_directions(10, 0, 4)
+
+
+def test_chunk_plan_partition(S):
+    """Host logic of ops.ChunkedRollout: sub-batches are contiguous, cover the batch exactly, never split
+    the environments of one direction, and the time chunks are 64-aligned and sum to H."""
+    import itertools
+    for B, unit, n_sub, H, chunk in itertools.product((64, 1000, 65536), (1, 2, 8), (1, 3, 16, 5000), (1, 64, 1000),
+                                                      (64, 128, 256)):
+        if B % unit:
+            continue
+        subs, lens = S.ops.plan_chunks(B, unit, n_sub, H, chunk)
+        assert subs[0][0] == 0 and subs[-1][1] == B and len(subs) <= min(n_sub, B // unit)
+        assert all(a[1] == b[0] for a, b in zip(subs, subs[1:]))
+        assert all((hi - lo) % unit == 0 and hi > lo for lo, hi in subs)
+        assert max(hi - lo for lo, hi in subs) - min(hi - lo for lo, hi in subs) <= unit
+        assert sum(lens) == H and all(L == chunk for L in lens[:-1]) and 0 < lens[-1] <= chunk
+    import pytest
+    with pytest.raises(ValueError):
+        S.ops.plan_chunks(128, 1, 4, 1000, 100)   # not a multiple of 64
+    with pytest.raises(ValueError):
+        S.ops.plan_chunks(130, 4, 4, 1000, 64)    # would split a direction
