@@ -46,7 +46,7 @@ def main():
     B, H = 65536, 1000
     actions = torch.as_tensor(rng.uniform(-5, 5, (B, 2))).cuda()
     ref = S.ops.rollout(p, H, actions=actions, want_final=True)
-    for n_sub, chunk in ((1, 1000), (16, 64), (32, 64), (64, 64), (128, 64), (32, 128), (64, 128), (24, 64), (37, 64)):
+    for n_sub, chunk in ((1, 1000), (8, 64), (16, 64), (32, 64), (16, 128), (32, 128)):
         enqueue, rets, state = build(p, actions, H, n_sub, chunk)
         enqueue()
         torch.cuda.synchronize()
