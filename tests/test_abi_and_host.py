@@ -60,6 +60,13 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower(), (dirpath, f)
+    # examples/ and tools/ are not product code either way, but they must not lean on the checker
+    for sub in ("examples", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".sh")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert "import oracle" not in src and "from oracle" not in src, (dirpath, f)
 
 
 def test_parameters_and_threshold(S):
