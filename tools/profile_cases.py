@@ -6,6 +6,7 @@ cases:  n3_fixed   BASELINE config[1]: n=3, 65,536 envs, fixed actions, H=1000
         n5_v2      BASELINE config[2]: n=5, ARS V2 + moments, 1,024 directions (2,048 envs), H=1000
         n10_grp    BASELINE config[4] per-GPU share at 8 GPUs: n=10, 512 directions x 2 x 128 rollouts
                    (131,072 envs), V2 + moments, H=1000
+        step_n3    batched single step (swm_step_batched), n=3, 4,194,304 envs: the HBM-bound entry point
         n3_safe    BASELINE config[3]: n=3, 256 directions, per-step screened rollouts, H=1000
 Prints the CUDA-event time per launch.
 """
@@ -40,6 +41,14 @@ def main():
         fn = lambda: S.ops.rollout(p, H, B=B, base_policy=W, nu=0.01, seed=1, mean=mean, inv_sigma=inv,
                                    stats_pivot=piv, rollouts_per_policy=R,
                                    init_perturb=1e-2 if R > 1 else 0.0)
+    elif case == "step_n3":
+        p = S.make_params(n=3)
+        B = 1 << 22
+        st = torch.as_tensor(rng.normal(size=(B, 8))).cuda()
+        ac = torch.as_tensor(rng.uniform(-5, 5, (B, 2))).cuda()
+        o = torch.empty_like(st)
+        H = 1
+        fn = lambda: S.ops.step_batched(p, st, ac, out=o)
     elif case == "n3_safe":
         p = S.make_params(n=3, l_i=0.8, m_i=1.2, k=10.2)
         sim = S.make_params(n=3, l_i=0.8006, m_i=1.2006, k=10.2006)
