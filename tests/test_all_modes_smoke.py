@@ -53,3 +53,55 @@ def test_no_out_of_bounds_writes_canaries(S, n):
     for name, (big, view) in list(bufs.items()) + [("step_state", (sbig, sview)), ("step_reward", (rbig, rview))]:
         assert bool((big[:PAD] == SENT).all()) and bool((big[-PAD:] == SENT).all()), (n, name)
         assert not bool((view == SENT).any()), (n, name)  # and the buffer itself was fully written
+
+
+def test_no_out_of_bounds_writes_ars_kernels(S):
+    """Same guard-zone check for the ARS bookkeeping kernels (ranking, update, statistics, reductions, Philox
+    table, batched select_action, learning-curve record) at awkward sizes."""
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(3)
+    SENT, PAD = -777.25, 2048
+
+    def guarded(shape, dtype=torch.float64, sent=SENT):
+        numel = int(np.prod(shape))
+        big = torch.full((numel + 2 * PAD,), sent, dtype=dtype, device="cuda")
+        return big, big[PAD:PAD + numel].view(*shape)
+
+    n, N, R = 7, 37, 3
+    no, ws = 2 * n + 2, (n - 1) * (2 * n + 2)
+    checks = []
+    rets = torch.as_tensor(rng.normal(size=2 * N)).cuda()
+    ob, order = guarded((N,), torch.int32, -7)
+    S.ops.ars_topb(rets, out=order)
+    checks.append(("order", ob, order, -7))
+    Wb, W = guarded((ws,))
+    W.zero_()
+    sb, sig = guarded((1,))
+    S.ops.ars_update(W, rets, N, order=order, n_order=11, alpha=0.1, seed=5, sigma_out=sig)
+    checks += [("W", Wb, W, SENT), ("sigma", sb, sig, SENT)]
+    part = torch.as_tensor(rng.normal(size=(5, 2, no))).cuda()
+    rb, rec = guarded((1 + 2 * no,))
+    S.ops.stats_finalize(part, 1234.0, S.ops.reset_state(n), out=rec)
+    checks.append(("record", rb, rec, SENT))
+    mb, mean = guarded((no,))
+    ib, inv = guarded((no,))
+    running = torch.zeros(1 + 2 * no, dtype=torch.float64, device="cuda")
+    S.ops.stats_merge(running, rec.reshape(1, -1).clone(), mean, inv)
+    checks += [("mean", mb, mean, SENT), ("inv_sigma", ib, inv, SENT)]
+    gb, grp = guarded((2 * N,))
+    S.ops.reduce_returns(torch.as_tensor(rng.normal(size=2 * N * R)).cuda(), R, out=grp)
+    checks.append(("reduced", gb, grp, SENT))
+    kb, mask = guarded((N,), torch.int32, -7)
+    nb, npass = guarded((1,), torch.int32, -7)
+    S.ops.screen_mask(rets, 0.0, mask, npass)
+    checks += [("mask", kb, mask, -7), ("n_pass", nb, npass, -7)]
+    cb, curve = guarded((9,))
+    curve.fill_(0.0)
+    S.ops.record_nanmean(rets, curve, torch.full((1,), 100, dtype=torch.int32, device="cuda"))  # clamps to the last slot
+    checks.append(("curve", cb, curve, SENT))
+    torch.cuda.synchronize()
+    for name, big, view, sent in checks:
+        assert bool((big[:PAD] == sent).all()) and bool((big[-PAD:] == sent).all()), name
+        assert not bool((view == sent).any()), name
+    assert float(curve[8]) == float(torch.nanmean(rets)) or abs(float(curve[8]) - float(rets.mean())) < 1e-12
