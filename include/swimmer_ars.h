@@ -33,7 +33,7 @@ extern "C" {
 #define SWM_API
 #endif
 
-#define SWM_ABI_VERSION 2
+#define SWM_ABI_VERSION 3
 #define SWM_MIN_SEGMENTS 2
 #define SWM_MAX_SEGMENTS 10
 
@@ -72,6 +72,16 @@ typedef enum {
   SWM_POLICY_DELTAS = 3        /* as PHILOX but delta_k is read from deltas[D, (n-1)(2n+2)] (row q/2):
                                   lets a caller replay the reference's own MT19937 draws */
 } swm_policy_mode;
+
+/* Which rollout kernel runs a launch.  Both implement the same equations and differ by rounding only
+ * (summation order); AUTO picks LANES for batches too small to fill the chip with one thread per env. */
+typedef enum {
+  SWM_KERNEL_AUTO = 0,
+  SWM_KERNEL_THREAD = 1, /* one thread = one environment (throughput: BASELINE configs 2 and 5) */
+  SWM_KERNEL_LANES = 2   /* one environment spread over 4/8/16 lanes, lane = segment (latency: the 2,048-env
+                            ARS iteration of config 3, the 512-env safe-exploration rollouts of config 4);
+                            gym dynamics without per-step screening / clipping, else SWM_ERR_UNSUPPORTED */
+} swm_rollout_kernel;
 
 /* Distribution of the Philox perturbations. */
 typedef enum {
@@ -148,7 +158,7 @@ typedef struct {
                                    next) and sub-batches on several streams, which removes the quantisation of
                                    mid-size batches over SM sub-partitions; chunk lengths that are multiples of 64
                                    keep the visited states bit-identical to the single launch. */
-  int32_t _pad2;
+  int32_t kernel;               /* swm_rollout_kernel: 0 = chosen from (B, n, SM count) */
 } swm_rollout_t;
 
 SWM_API int swm_abi_version(void);
@@ -180,8 +190,12 @@ SWM_API int swm_accelerations_batched(const swm_params_t* params, int variant, c
                               const double* action, double* acc, int64_t B, void* stream);
 
 SWM_API int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg, void* stream);
-/* number of per-block rows the rollout kernel writes into stats_partial for B envs */
+/* number of per-block rows the rollout kernel writes into stats_partial for B envs (depends on the kernel
+ * swm_rollout will choose for this cfg on the current device) */
 SWM_API int64_t swm_rollout_stats_blocks(const swm_params_t* params, const swm_rollout_t* cfg);
+/* which kernel swm_rollout would run for this cfg on the current device: SWM_KERNEL_THREAD / _LANES,
+ * or a negative swm_status */
+SWM_API int swm_rollout_kernel_choice(const swm_params_t* params, const swm_rollout_t* cfg);
 
 /* Deterministic Welford bookkeeping for ARS V2 (replaces np.mean / np.cov over the growing
  * saved_states list, ars/ars_agent.py:179-182).  A statistics record is

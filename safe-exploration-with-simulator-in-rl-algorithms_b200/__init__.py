@@ -10,8 +10,8 @@ New batched surface: ops.step_batched / ops.rollout / ArsEngine (see include/swi
 All arithmetic runs in libswimmer_ars.so (hand-written sm_100a CUDA); there is no CPU fallback.
 """
 from . import _lib, ops  # noqa: F401
-from ._lib import (ARS_AGENT, ARS_RLGLUE, ARS_TOPB, DELTA_01, DELTA_PM1, GYM, RLGLUE,  # noqa: F401
-                   SwimmerLibError, build_library, make_params)
+from ._lib import (ARS_AGENT, ARS_RLGLUE, ARS_TOPB, DELTA_01, DELTA_PM1, GYM, KERNEL_AUTO, KERNEL_LANES,  # noqa: F401
+                   KERNEL_THREAD, RLGLUE, SwimmerLibError, build_library, make_params)
 from .ars_agent import ARSAgent  # noqa: F401
 from .database import Database, pick_sub_database  # noqa: F401
 from .engine import ArsEngine  # noqa: F401

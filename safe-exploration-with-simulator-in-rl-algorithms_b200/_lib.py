@@ -17,8 +17,9 @@ GYM, RLGLUE = 0, 1
 POLICY_FIXED_ACTION, POLICY_EXPLICIT, POLICY_PHILOX, POLICY_DELTAS = 0, 1, 2, 3
 DELTA_PM1, DELTA_01 = 0, 1
 ARS_AGENT, ARS_TOPB, ARS_RLGLUE = 0, 1, 2
+KERNEL_AUTO, KERNEL_THREAD, KERNEL_LANES = 0, 1, 2  # swm_rollout_kernel
 MIN_SEGMENTS, MAX_SEGMENTS = 2, 10
-ABI_VERSION = 2  # include/swimmer_ars.h SWM_ABI_VERSION
+ABI_VERSION = 3  # include/swimmer_ars.h SWM_ABI_VERSION
 MAX_MODELS_PER_STEP = 24  # SWM_MAX_MODELS_PER_STEP
 
 _dp = ctypes.c_void_p
@@ -50,7 +51,7 @@ class SwmRollout(ctypes.Structure):
                 ("inv_sigma", _dp), ("init_state", _dp), ("init_state_count", ctypes.c_int64),
                 ("init_perturb", ctypes.c_double), ("returns", _dp), ("final_state", _dp),
                 ("trajectory", _dp), ("stats_partial", _dp), ("stats_pivot", _dp),
-                ("screen", SwmScreen), ("accumulate_returns", ctypes.c_int32), ("_pad2", ctypes.c_int32)]
+                ("screen", SwmScreen), ("accumulate_returns", ctypes.c_int32), ("kernel", ctypes.c_int32)]
 
 
 class SwimmerLibError(RuntimeError):
@@ -94,6 +95,7 @@ def lib():
     L.swm_rollout.argtypes = [pp, ctypes.POINTER(SwmRollout), _dp]
     L.swm_rollout_stats_blocks.argtypes = [pp, ctypes.POINTER(SwmRollout)]
     L.swm_rollout_stats_blocks.restype = i64
+    L.swm_rollout_kernel_choice.argtypes = [pp, ctypes.POINTER(SwmRollout)]
     L.swm_stats_finalize.argtypes = [_dp, i64, c_int, dbl, _dp, _dp, _dp, _dp]
     L.swm_stats_merge.argtypes = [_dp, _dp, c_int, c_int, _dp, _dp, _dp]
     L.swm_reduce_returns.argtypes = [_dp, i64, c_int, _dp, _dp]

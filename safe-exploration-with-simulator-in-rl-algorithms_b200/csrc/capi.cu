@@ -5,7 +5,7 @@
 #include <string.h>
 
 #include "errors.cuh"
-#include "launch.cuh"
+#include "lane_launch.cuh"
 
 using namespace swm;
 
@@ -148,22 +148,28 @@ extern "C" int swm_accelerations_batched(const swm_params_t* params, int variant
   return step_common(params, variant, true, state, action, acc, nullptr, B, stream);
 }
 
-extern "C" int64_t swm_rollout_stats_blocks(const swm_params_t* params, const swm_rollout_t* cfg) {
-  (void)params;
-  if (!cfg || cfg->B < 1) return 0;
-  return (cfg->B + kRolloutBlock - 1) / kRolloutBlock;
+namespace {
+
+int sm_count_cached() {
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    sms[dev] = v;
+  }
+  return sms[dev];
 }
 
-extern "C" int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg, void* stream) {
+// Validates cfg and fills the kernel arguments; returns SWM_OK or an error.
+int build_rollout_args(const swm_params_t* params, const swm_rollout_t* cfg, RolloutArgs& a, RolloutFlags& f) {
   if (!params_ok(params) || !cfg) return SWM_ERR_BAD_ARG;
   if (cfg->B < 0 || cfg->H < 0 || cfg->rollouts_per_policy < 1) return SWM_ERR_BAD_ARG;
   if (cfg->variant != SWM_DYN_GYM && cfg->variant != SWM_DYN_RLGLUE) return SWM_ERR_BAD_ARG;
-  if (cfg->B == 0) return SWM_OK;
-  if (!cfg->returns) return SWM_ERR_BAD_ARG;
+  if (cfg->kernel < SWM_KERNEL_AUTO || cfg->kernel > SWM_KERNEL_LANES) return SWM_ERR_BAD_ARG;
   if (cfg->B > (int64_t)kRolloutBlock * 0x7fffffffLL) return SWM_ERR_BAD_ARG;
-  RolloutArgs a;
   memset(&a, 0, sizeof(a));
-  RolloutFlags f;
   f.variant = cfg->variant;
   f.norm = cfg->normalize != 0;
   f.stats = cfg->stats_partial != nullptr;
@@ -171,17 +177,14 @@ extern "C" int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg,
   f.group_w = (cfg->rollouts_per_policy % 32) == 0;
   switch (cfg->policy_mode) {
     case SWM_POLICY_FIXED_ACTION:
-      if (!cfg->actions) return SWM_ERR_BAD_ARG;
       f.linear = false;
       break;
     case SWM_POLICY_EXPLICIT:
     case SWM_POLICY_PHILOX:
     case SWM_POLICY_DELTAS:
-      if (!cfg->policies) return SWM_ERR_BAD_ARG;
       if (cfg->B % cfg->rollouts_per_policy != 0) return SWM_ERR_BAD_ARG;
       if (cfg->policy_mode != SWM_POLICY_EXPLICIT && ((cfg->B / cfg->rollouts_per_policy) % 2) != 0)
         return SWM_ERR_BAD_ARG;  // +delta / -delta pairs
-      if (cfg->policy_mode == SWM_POLICY_DELTAS && !cfg->deltas) return SWM_ERR_BAD_ARG;
       if (cfg->policy_mode == SWM_POLICY_EXPLICIT && cfg->dir_mask) return SWM_ERR_BAD_ARG;
       f.linear = true;
       break;
@@ -189,8 +192,6 @@ extern "C" int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg,
       return SWM_ERR_BAD_ARG;
   }
   if (!f.linear && cfg->dir_mask) return SWM_ERR_BAD_ARG;
-  if (f.norm && (!cfg->mean || !cfg->inv_sigma)) return SWM_ERR_BAD_ARG;
-  if (f.stats && !cfg->stats_pivot) return SWM_ERR_BAD_ARG;
   if (cfg->init_state && cfg->init_state_count < 1) return SWM_ERR_BAD_ARG;
   if (f.screen) {
     if (!params_ok(&cfg->screen.sim) || cfg->screen.sim.n != params->n) return SWM_ERR_BAD_ARG;
@@ -227,7 +228,68 @@ extern "C" int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg,
   a.violations = cfg->screen.violations;
   a.frozen_at = cfg->screen.frozen_at;
   a.accumulate = cfg->accumulate_returns;
+  return SWM_OK;
+}
+
+// AUTO: the lane-split kernel wins while its warps (B * L / 32) still find a sub-partition of their own,
+// or at most share one with a second warp: measured crossover, tools/lane_split_sweep.py.  It is tuned for
+// chains of up to 7 segments (8 lanes per environment).
+constexpr double kLaneSplitMaxWarpsPerSmsp = 2.0;
+
+int choose_kernel(int n, const swm_rollout_t* cfg, const RolloutArgs& a, const RolloutFlags& f) {
+  const bool ok = lane_split_supported(a, f);
+  if (cfg->kernel == SWM_KERNEL_LANES) return ok ? SWM_KERNEL_LANES : SWM_ERR_UNSUPPORTED;
+  if (cfg->kernel == SWM_KERNEL_THREAD || !ok || n > 7) return SWM_KERNEL_THREAD;
+  const int per_warp = 32 / lane_split_lanes(n);
+  const double warps = (double)((cfg->B + per_warp - 1) / per_warp);
+  return warps <= kLaneSplitMaxWarpsPerSmsp * 4.0 * sm_count_cached() ? SWM_KERNEL_LANES : SWM_KERNEL_THREAD;
+}
+
+}  // namespace
+
+extern "C" int swm_rollout_kernel_choice(const swm_params_t* params, const swm_rollout_t* cfg) {
+  RolloutArgs a;
+  RolloutFlags f;
+  const int rc = build_rollout_args(params, cfg, a, f);
+  if (rc != SWM_OK) return rc;
+  return choose_kernel(params->n, cfg, a, f);
+}
+
+extern "C" int64_t swm_rollout_stats_blocks(const swm_params_t* params, const swm_rollout_t* cfg) {
+  if (!cfg || cfg->B < 1) return 0;
+  // the row count only depends on the kernel choice, which never looks at the output pointers
+  swm_rollout_t probe = *cfg;
+  static double dummy;
+  probe.stats_partial = &dummy;
+  if (swm_rollout_kernel_choice(params, &probe) == SWM_KERNEL_LANES) {
+    const int per_warp = 32 / lane_split_lanes(params->n);
+    return (cfg->B + per_warp - 1) / per_warp;
+  }
+  return (cfg->B + kRolloutBlock - 1) / kRolloutBlock;
+}
+
+extern "C" int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg, void* stream) {
+  RolloutArgs a;
+  RolloutFlags f;
+  if (params_ok(params) && cfg && cfg->B == 0 && cfg->H >= 0 && cfg->rollouts_per_policy >= 1 &&
+      (cfg->variant == SWM_DYN_GYM || cfg->variant == SWM_DYN_RLGLUE))
+    return SWM_OK;  // empty batch: nothing to do, pointers may be NULL
+  const int rc = build_rollout_args(params, cfg, a, f);
+  if (rc != SWM_OK) return rc;
+  if (!cfg->returns) return SWM_ERR_BAD_ARG;
+  if (!f.linear && !cfg->actions) return SWM_ERR_BAD_ARG;
+  if (f.linear && !cfg->policies) return SWM_ERR_BAD_ARG;
+  if (cfg->policy_mode == SWM_POLICY_DELTAS && !cfg->deltas) return SWM_ERR_BAD_ARG;
+  if (f.norm && (!cfg->mean || !cfg->inv_sigma)) return SWM_ERR_BAD_ARG;
+  if (f.stats && !cfg->stats_pivot) return SWM_ERR_BAD_ARG;
+  const int kernel = choose_kernel(params->n, cfg, a, f);
+  if (kernel < 0) return kernel;
   cudaStream_t st = (cudaStream_t)stream;
+  if (kernel == SWM_KERNEL_LANES) {
+#define CALL(K) launch_lane_rollout_n<K>(a, f, st)
+    SWM_DISPATCH_N(params->n, CALL)
+#undef CALL
+  }
 #define CALL(K) launch_rollout_n<K>(a, f, st)
   SWM_DISPATCH_N(params->n, CALL)
 #undef CALL

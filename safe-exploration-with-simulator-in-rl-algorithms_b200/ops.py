@@ -15,7 +15,7 @@ from ._lib import (ARS_AGENT, ARS_RLGLUE, ARS_TOPB, DELTA_01, DELTA_PM1, GYM, PO
 
 __all__ = ["step_batched", "step_batched_models", "accelerations_batched", "rollout", "RolloutResult", "ChunkedRollout", "plan_chunks", "philox_deltas",
            "ars_topb", "ars_update", "counter_add", "record_nanmean", "stats_finalize", "stats_merge", "reduce_returns", "screen_mask", "policy_actions", "update_args",
-           "fp64_probe", "obs_dim", "act_dim", "policy_size", "reset_state"]
+           "fp64_probe", "obs_dim", "act_dim", "policy_size", "reset_state", "lane_split_envs_per_warp"]
 
 
 def obs_dim(n):
@@ -28,6 +28,12 @@ def act_dim(n):
 
 def policy_size(n):
     return (n - 1) * (2 * n + 2)
+
+
+def lane_split_envs_per_warp(n):
+    """Environments per warp (= per stats_partial row) of the lane-split rollout kernel: 32 / L with
+    L = 4, 8 or 16 lanes per environment (csrc/lane_rollout.cuh LaneSplit)."""
+    return 32 // (4 if n + 1 <= 4 else 8 if n + 1 <= 8 else 16)
 
 
 def reset_state(n, variant=GYM, device="cuda"):
@@ -116,7 +122,7 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
             seed=0, iteration=0, iteration_dev=None, dir0=0, delta_dist=DELTA_PM1, rollouts_per_policy=1, mean=None,
             inv_sigma=None, clip_actions=False, init_state=None, want_final=False,
             want_trajectory=False, stats_pivot=None, screen=None, out=None, device=None,
-            accumulate_returns=False):
+            accumulate_returns=False, kernel=0):
     """One fused H-step rollout of B environments (swm_rollout).
 
     Exactly one of
@@ -129,6 +135,8 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
     screen = dict(sim_params=..., sim_thresh=..., real_thresh=...) enables Safe_ARS screening.
     stats_pivot[2n+2] enables the V2 moment accumulation.  `out` may carry preallocated
     tensors (returns, final_state, trajectory, stats_partial) to stay allocation-free in loops.
+    kernel: _lib.KERNEL_AUTO (chosen from B, n and the SM count) / KERNEL_THREAD (one thread per
+    environment) / KERNEL_LANES (one environment over 4/8/16 lanes; small batches).
     """
     _lib.require_cuda()
     n = params.n
@@ -173,6 +181,8 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
     cfg.rollouts_per_policy = int(rollouts_per_policy)
     cfg.clip_actions = int(bool(clip_actions))
     cfg.accumulate_returns = int(bool(accumulate_returns))
+    cfg.kernel = int(kernel)
+    cfg.screen.enabled = int(screen is not None)  # before swm_rollout_stats_blocks: it decides the kernel
     cfg.nu = float(nu)
     cfg.init_perturb = float(init_perturb)
     cfg.philox.seed, cfg.philox.iteration = int(seed) & (2 ** 64 - 1), int(iteration)
@@ -322,7 +332,8 @@ class ChunkedRollout:
                     rollout(self.params, L, variant=self.variant, rollouts_per_policy=self.R,
                             init_state=None if c == 0 else self.state[lo:hi],
                             init_perturb=init_perturb if c == 0 else 0.0, want_final=True,
-                            stats_pivot=self.stats_pivot, accumulate_returns=c > 0, out=out, **src, **call)
+                            stats_pivot=self.stats_pivot, accumulate_returns=c > 0, out=out,
+                            kernel=_lib.KERNEL_THREAD, **src, **call)
         for st in self.streams:
             cur.wait_stream(st)
         res = RolloutResult()

@@ -36,7 +36,7 @@ def test_struct_layouts_match_build(S):
     assert L.swm_abi_struct_sizes(*[ctypes.byref(x) for x in v]) == 0
     assert [x.value for x in v] == [ctypes.sizeof(S._lib.SwmParams), ctypes.sizeof(S._lib.SwmPhilox),
                                     ctypes.sizeof(S._lib.SwmScreen), ctypes.sizeof(S._lib.SwmRollout)]
-    assert L.swm_abi_version() == S._lib.ABI_VERSION == 2
+    assert L.swm_abi_version() == S._lib.ABI_VERSION == 3
     assert L.swm_strerror(-2) == b"unsupported configuration"
 
 

@@ -34,14 +34,18 @@ def test_no_out_of_bounds_writes_canaries(S, n):
         return big, big[PAD:PAD + numel].view(*shape)
 
     bufs = {}
-    for name, shape in (("returns", (B,)), ("final_state", (B, no)), ("trajectory", (H, B, no)),
-                        ("stats_partial", ((B + 63) // 64, 2, no))):
-        bufs[name] = guarded(shape)
-    out = {k: v[1] for k, v in bufs.items()}
     W = torch.as_tensor(rng.uniform(-1, 1, ws) * 0.1).cuda()
     mean = torch.zeros(no, dtype=torch.float64, device="cuda")
-    S.ops.rollout(p, H, B=B, base_policy=W, nu=0.05, seed=1, mean=mean, inv_sigma=torch.ones_like(mean),
-                  stats_pivot=S.ops.reset_state(n), want_final=True, want_trajectory=True, out=out)
+    # both rollout kernels: one thread per environment (64 per block) and lane-split (32 / L per warp)
+    for tag, kern, per_block in (("thread", S.KERNEL_THREAD, 64), ("lanes", S.KERNEL_LANES, S.ops.lane_split_envs_per_warp(n))):
+        kb = {}
+        for name, shape in (("returns", (B,)), ("final_state", (B, no)), ("trajectory", (H, B, no)),
+                            ("stats_partial", ((B + per_block - 1) // per_block, 2, no))):
+            kb[name] = guarded(shape)
+        S.ops.rollout(p, H, B=B, base_policy=W, nu=0.05, seed=1, mean=mean, inv_sigma=torch.ones_like(mean),
+                      stats_pivot=S.ops.reset_state(n), want_final=True, want_trajectory=True, kernel=kern,
+                      out={k: v[1] for k, v in kb.items()})
+        bufs.update({tag + "_" + k: v for k, v in kb.items()})
     sbig, sview = guarded((B, no))
     rbig, rview = guarded((B,))
     st = torch.as_tensor(rng.normal(size=(B, no))).cuda()

@@ -331,7 +331,9 @@ def test_chunked_rollout_equals_single_launch(S, case):
     single_kw.update(extra)
     if "actions" not in kw and "policies" not in kw:
         single_kw["B"] = B
-    ref = S.ops.rollout(p, H, want_final=True, dir0=5 if "base_policy" in kw else 0, **single_kw)
+    # the chunked schedule launches the one-thread-per-environment kernel (bit-identical chaining)
+    ref = S.ops.rollout(p, H, want_final=True, dir0=5 if "base_policy" in kw else 0, kernel=S.KERNEL_THREAD,
+                        **single_kw)
     for n_sub, chunk in ((1, 64), (3, 64), (4, 128)):
         plan = S.ops.ChunkedRollout(p, H, B=B, n_sub=n_sub, chunk=chunk, **kw, **extra)
         for _ in range(2):  # re-running reuses the buffers

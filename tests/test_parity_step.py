@@ -233,7 +233,8 @@ def test_rollout_plan_through_the_env_surface(S):
     ac = torch.as_tensor(np.random.default_rng(2).uniform(-5, 5, (3000, 2))).cuda()
     plan = env.rollout_plan(200, n_sub=4, chunk=64, actions=ac)
     got = plan.run()
-    ref = env.rollout_batched(200, actions=ac, want_final=True)
+    # the chunked schedule runs the one-thread-per-environment kernel: bit-identical to its single launch
+    ref = env.rollout_batched(200, actions=ac, want_final=True, kernel=S.KERNEL_THREAD)
     assert torch.equal(got.final_state, ref.final_state) and plan.launches == 4 * 4
     np.testing.assert_allclose(got.returns.cpu().numpy(), ref.returns.cpu().numpy(), rtol=1e-12, atol=1e-13)
 

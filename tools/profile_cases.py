@@ -4,6 +4,8 @@
 
 cases:  n3_fixed   BASELINE config[1]: n=3, 65,536 envs, fixed actions, H=1000
         n5_v2      BASELINE config[2]: n=5, ARS V2 + moments, 1,024 directions (2,048 envs), H=1000
+                   (AUTO kernel choice = lane-split; n5_v2_thread forces one thread per environment,
+                   n5_v2_256 is the per-GPU share at 8 GPUs)
         n10_grp    BASELINE config[4] per-GPU share at 8 GPUs: n=10, 512 directions x 2 x 128 rollouts
                    (131,072 envs), V2 + moments, H=1000
         step_n3    batched single step (swm_step_batched), n=3, 4,194,304 envs: the HBM-bound entry point
@@ -29,8 +31,9 @@ def main():
         ac = torch.as_tensor(rng.uniform(-5, 5, (65536, 2))).cuda()
         fn = lambda: S.ops.rollout(p, H, actions=ac, want_final=True)
         B = 65536
-    elif case in ("n5_v2", "n10_grp"):
-        n, D, R = (5, 1024, 1) if case == "n5_v2" else (10, 512, 128)
+    elif case in ("n5_v2", "n5_v2_thread", "n5_v2_256", "n10_grp"):
+        n, D, R = (10, 512, 128) if case == "n10_grp" else (5, 128 if case == "n5_v2_256" else 1024, 1)
+        kern = S.KERNEL_THREAD if case == "n5_v2_thread" else S.KERNEL_AUTO
         p = S.make_params(n=n)
         no, ws = 2 * n + 2, (n - 1) * (2 * n + 2)
         W = torch.as_tensor(rng.uniform(-1, 1, ws) * 0.05).cuda()
@@ -39,7 +42,7 @@ def main():
         piv = S.ops.reset_state(n)
         B = 2 * D * R
         fn = lambda: S.ops.rollout(p, H, B=B, base_policy=W, nu=0.01, seed=1, mean=mean, inv_sigma=inv,
-                                   stats_pivot=piv, rollouts_per_policy=R,
+                                   stats_pivot=piv, rollouts_per_policy=R, kernel=kern,
                                    init_perturb=1e-2 if R > 1 else 0.0)
     elif case == "step_n3":
         p = S.make_params(n=3)
