@@ -269,6 +269,52 @@ SWM_API int swm_counter_add(uint32_t* counter, uint32_t inc, void* stream);
 SWM_API int swm_record_nanmean(const double* x, int n, double* curve, const uint32_t* index,
                                uint32_t capacity, void* stream);
 
+/* ---- Per-iteration record exchange of a sharded ARS iteration --------------------------------
+ * Directions are sharded contiguously over `world` ranks (one process per GPU).  Each iteration every rank
+ * packs ONE record [returns (2 n_local) | mask (n_local, optional) | count, mean[F], M2[F]], all ranks
+ * exchange them, and every rank unpacks returns_all[2N] / mask_all[N] / records[world, 1+2F] for the
+ * redundant, bit-identical ranking, update and Welford merge (replaces the 2N sequential rollouts'
+ * `rewards.append` of ars_agent.py:161-172 and the cumulative np.mean/np.cov of :179-182 across ranks).
+ *
+ * swm_ars_pack_exchange does pack + exchange + unpack in ONE kernel launch:
+ *   - h == NULL, gathered_world <= 1: single process, pack and unpack only;
+ *   - h != NULL (world > 1): the record is stored into every rank's gather buffer over NVLink through
+ *     CUDA-IPC peer pointers, epoch flags are published and awaited inside the kernel -- no NCCL call on
+ *     the data path, so the whole iteration can be captured in a CUDA graph.  Setup (once): every rank
+ *     calls swm_exchange_create, exports swm_exchange_ipc_handle (SWM_IPC_HANDLE_BYTES bytes), the host
+ *     layer all-gathers the handles (torch.distributed / MPI / files) and passes the table to
+ *     swm_exchange_open_peers.  A peer that does not answer within ~2 s sets a sticky status
+ *     (swm_exchange_status) instead of hanging the device;
+ *   - collective fallback (no peer access): call once with record_out set and gathered_world = world
+ *     (pack only), all-gather record_out with the host's collective, then call with gathered_in. */
+typedef struct swm_exchange swm_exchange_t;
+#define SWM_IPC_HANDLE_BYTES 64
+typedef struct {
+  const double* returns_local;  /* [2 n_local R] per-env returns of this rank's rollouts */
+  int32_t n_local;              /* directions owned by this rank */
+  int32_t rollouts_per_policy;  /* R: record carries the mean over the R rollouts of a policy */
+  const int32_t* mask_local;    /* [n_local] or NULL: screening mask of this rank's directions */
+  const double* stats_partial;  /* [n_blocks, 2, F] from swm_rollout, or NULL (count 0) */
+  int64_t n_blocks;
+  int32_t n_features;           /* F = 2n+2, or 0 for ARS V1 (no statistics in the record) */
+  int32_t gathered_world;       /* ranks in gathered_in / expected by the collective fallback */
+  double samples;               /* states behind stats_partial (x *units if given) */
+  const int32_t* units;         /* optional device int32 multiplier of samples */
+  const double* pivot;          /* [F] */
+  double* returns_all;          /* out [2 N] (NULL: pack only) */
+  int32_t* mask_all;            /* out [N] or NULL */
+  double* records;              /* out [world, 1+2F] or NULL */
+  double* record_out;           /* out, optional: this rank's packed record [swm_pack_record_doubles] */
+  const double* gathered_in;    /* in, optional: [gathered_world, record_doubles]; skips pack + exchange */
+} swm_pack_t;
+SWM_API int64_t swm_pack_record_doubles(int n_local, int has_mask, int n_features);
+SWM_API int swm_exchange_create(int world, int rank, int64_t record_doubles, swm_exchange_t** out);
+SWM_API int swm_exchange_ipc_handle(swm_exchange_t* h, void* handle_out /* host, SWM_IPC_HANDLE_BYTES */);
+SWM_API int swm_exchange_open_peers(swm_exchange_t* h, const void* handles /* host, world x SWM_IPC_HANDLE_BYTES */);
+SWM_API int swm_exchange_status(swm_exchange_t* h, uint64_t* epoch, uint64_t* status); /* host out; synchronises */
+SWM_API int swm_exchange_destroy(swm_exchange_t* h);
+SWM_API int swm_ars_pack_exchange(swm_exchange_t* h, const swm_pack_t* p, void* stream);
+
 /* FP64 pipe probe: every thread runs `iters` x 8 independent DFMA chains; returns through
  * *flops_out (host) the number of floating-point operations executed (2 per DFMA).  Used by
  * bench.py to measure the FP64 roofline denominator on the box (MEASURED_PEAKS.json has none). */

@@ -54,6 +54,18 @@ class SwmRollout(ctypes.Structure):
                 ("screen", SwmScreen), ("accumulate_returns", ctypes.c_int32), ("kernel", ctypes.c_int32)]
 
 
+class SwmPack(ctypes.Structure):
+    """swm_pack_t (include/swimmer_ars.h): arguments of the fused pack + exchange + unpack launch."""
+    _fields_ = [("returns_local", _dp), ("n_local", ctypes.c_int32), ("rollouts_per_policy", ctypes.c_int32),
+                ("mask_local", _dp), ("stats_partial", _dp), ("n_blocks", ctypes.c_int64),
+                ("n_features", ctypes.c_int32), ("gathered_world", ctypes.c_int32), ("samples", ctypes.c_double),
+                ("units", _dp), ("pivot", _dp), ("returns_all", _dp), ("mask_all", _dp), ("records", _dp),
+                ("record_out", _dp), ("gathered_in", _dp)]
+
+
+IPC_HANDLE_BYTES = 64  # SWM_IPC_HANDLE_BYTES
+
+
 class SwimmerLibError(RuntimeError):
     pass
 
@@ -109,6 +121,14 @@ def lib():
     L.swm_counter_add.argtypes = [_dp, ctypes.c_uint32, _dp]
     L.swm_record_nanmean.argtypes = [_dp, c_int, _dp, _dp, ctypes.c_uint32, _dp]
     L.swm_rlglue_set_params.argtypes = [pp]
+    L.swm_pack_record_doubles.argtypes = [c_int, c_int, c_int]
+    L.swm_pack_record_doubles.restype = i64
+    L.swm_exchange_create.argtypes = [c_int, c_int, i64, ctypes.POINTER(_dp)]
+    L.swm_exchange_ipc_handle.argtypes = [_dp, _dp]
+    L.swm_exchange_open_peers.argtypes = [_dp, _dp]
+    L.swm_exchange_status.argtypes = [_dp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    L.swm_exchange_destroy.argtypes = [_dp]
+    L.swm_ars_pack_exchange.argtypes = [_dp, ctypes.POINTER(SwmPack), _dp]
     if L.swm_abi_version() != ABI_VERSION:
         raise SwimmerLibError("ABI version mismatch")
     _lib = L

@@ -22,6 +22,8 @@ unless `keep_states=True` (D-6: the reference keeps every state ever seen).
 """
 import dataclasses
 
+import os
+
 import numpy as np
 import torch
 
@@ -207,6 +209,9 @@ class ARSAgent:
 try:  # optional: the reference decorates the class with @ray.remote (ars_agent.py:15)
     import ray as _ray
 
-    ARSAgent.remote = staticmethod(lambda *a, **k: _ray.remote(ARSAgent).remote(*a, **k))
+    # an actor without a GPU share would see CUDA_VISIBLE_DEVICES='' and fail in require_cuda(): by default
+    # eight agents share one GPU (ars/experiment.py runs one actor per seed)
+    ARSAgent.remote = staticmethod(lambda *a, **k: _ray.remote(
+        num_gpus=float(os.environ.get("SWM_RAY_NUM_GPUS", "0.125")))(ARSAgent).remote(*a, **k))
 except Exception:  # ray is not installed in this image
     pass

@@ -131,7 +131,9 @@ __global__ void screen_mask_kernel(const double* __restrict__ sim_returns, int N
   __shared__ double red[kArsBlock / 32];
   double c = 0.0;
   for (int k = threadIdx.x; k < N; k += kArsBlock) {
-    const bool skip = (sim_returns[2 * k] <= threshold) || (sim_returns[2 * k + 1] <= threshold);
+    // The reference skips on `reward <= sim_threshold`; a NaN simulator return (diverged simulation) compares
+    // false there and would be rolled out in the real world.  Declared deviation: NaN is screened out too.
+    const bool skip = !((sim_returns[2 * k] > threshold) && (sim_returns[2 * k + 1] > threshold));
     mask[k] = skip ? 0 : 1;
     c += skip ? 0.0 : 1.0;
   }
@@ -225,8 +227,12 @@ __global__ void stats_merge_kernel(double* __restrict__ running, const double* _
   running[1 + f] = ma;
   running[1 + F + f] = Ma;
   if (f == 0) running[0] = na;
-  if (mean_out) mean_out[f] = ma;
-  if (inv_sigma_out) inv_sigma_out[f] = 1.0 / sqrt(Ma / (na - 1.0));  // diag(np.cov)**(-1/2)
+  // ars_agent.py:179-182 only recomputes mean / cov `if len(rewards) > 0`: while nothing has been observed
+  // (every direction screened out so far) the initial mean = 0, cov = I stay in place; np.cov needs >= 2 samples
+  if (na >= 2.0) {
+    if (mean_out) mean_out[f] = ma;
+    if (inv_sigma_out) inv_sigma_out[f] = 1.0 / sqrt(Ma / (na - 1.0));  // diag(np.cov)**(-1/2)
+  }
 }
 
 __global__ void reduce_returns_kernel(const double* __restrict__ returns, long long n_groups, int R,

@@ -69,8 +69,8 @@ struct RolloutArgs {
 // ---------------------------------------------------------------------------------------------
 template <int N, int VARIANT, bool ACC_ONLY>
 __global__ void __launch_bounds__(kStepBlock)
-step_kernel(Phys P, const double* __restrict__ state_in, const double* __restrict__ action,
-            double* __restrict__ state_out, double* __restrict__ reward, long long B) {
+step_kernel(Phys P, const double* state_in, const double* __restrict__ action,
+            double* state_out, double* __restrict__ reward, long long B) {  // state_out may alias state_in
   constexpr int NO = 2 * N + 2, NA = N - 1;
   const long long e = (long long)blockIdx.x * kStepBlock + threadIdx.x;
   if (e >= B) return;
@@ -120,8 +120,8 @@ struct PhysSet {
 template <int N>
 __global__ void __launch_bounds__(kStepBlock)
 step_models_kernel(const __grid_constant__ PhysSet set, long long envs_per_model,
-                   const double* __restrict__ state_in, const double* __restrict__ action,
-                   double* __restrict__ state_out, double* __restrict__ reward, long long B) {
+                   const double* state_in, const double* __restrict__ action,
+                   double* state_out, double* __restrict__ reward, long long B) {  // state_out may alias state_in
   constexpr int NO = 2 * N + 2, NA = N - 1;
   const long long e = (long long)blockIdx.x * kStepBlock + threadIdx.x;
   if (e >= B) return;

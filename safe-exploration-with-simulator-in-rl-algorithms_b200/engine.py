@@ -4,9 +4,10 @@ ARSAgent.runOneIteration (ars/ars_agent.py:132-185) and Basic_ARS.train (safe_ar
 One iteration =
   1. [reward-constraint safe mode] 2N simulator rollouts -> screening mask        (swm_rollout, swm_screen_mask)
   2. 2N (x R) real rollouts, all in one fused kernel launch                        (swm_rollout)
-  3. [R > 1] per-direction mean return; [V2] per-rank moment record                (swm_reduce_returns, swm_stats_finalize)
-  4. [world > 1] ONE all-gather of the packed per-rank record over NCCL            (torch.distributed)
-  5. redundantly on every rank, bit-identically: top-b ranking, delta-weighted
+  3. ONE launch that packs this rank's record (per-direction mean returns, screening mask, V2 moment
+     record), exchanges it with every other rank over NVLink peer memory and unpacks all ranks'
+     records                                                                       (swm_ars_pack_exchange)
+  4. redundantly on every rank, bit-identically: top-b ranking, delta-weighted
      update with deltas regenerated from Philox, Welford merge in rank order       (swm_ars_topb, swm_ars_update, swm_stats_merge)
 
 Directions are sharded contiguously across ranks (rank r owns [r N/world, (r+1) N/world)); the
@@ -15,13 +16,16 @@ delta tensors never move.  Nothing in an iteration synchronises with the host.
 The iteration number that keys Philox lives in device memory (`iter_dev`, advanced by
 swm_counter_add at the end of the update), so the whole iteration is a fixed sequence of launches
 with fixed arguments: `use_graph=True` captures it once into a CUDA graph and replays it (one
-launch per iteration instead of ~10; single-process engines only).
+launch per iteration instead of 5-7).  Sharded engines are captured too: their exchange is a kernel
+(distributed.RecordExchange, transport "p2p"), not a collective; only the collective fallback
+(no peer access between the GPUs) enqueues eagerly.
 """
 import torch
 import torch.distributed as dist
 
 from . import _lib, ops
 from ._lib import ARS_AGENT, DELTA_PM1, GYM
+from .distributed import RecordExchange, RecordLayout
 
 
 class ArsEngine:
@@ -29,7 +33,8 @@ class ArsEngine:
                  rollouts_per_direction=1, seed=0, variant=GYM, delta_dist=DELTA_PM1,
                  clip_actions=False, init_perturb=0.0, initial_policy=None, group=None,
                  distributed=None, device=None, sim_params=None, sim_threshold=None,
-                 step_screen=None, use_graph=False, curve_capacity=0, rollout_chunks=None):
+                 step_screen=None, use_graph=False, curve_capacity=0, rollout_chunks=None, transport="auto",
+                 rollout_kernel=0):
         _lib.require_cuda()
         self.params, self.N, self.b, self.alpha, self.nu, self.H = params, int(N), int(b), alpha, nu, int(H)
         self.v2, self.semantics, self.R = bool(v2), semantics, int(rollouts_per_direction)
@@ -56,9 +61,7 @@ class ArsEngine:
         self.iter_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         # optional device-side learning curve: curve[j] = nanmean(returns of iteration j)
         self.curve = torch.full((int(curve_capacity),), float("nan"), **f64) if curve_capacity > 0 else None
-        # single-process engines only: capturing the NCCL all-gather next to eager collectives on the same
-        # communicator hung on the 2-GPU box (round 1), so sharded engines always enqueue eagerly
-        self.use_graph = bool(use_graph) and self.world == 1
+        self.rollout_kernel = int(rollout_kernel)  # _lib.KERNEL_AUTO / KERNEL_THREAD / KERNEL_LANES
         self._graph = None
         self._warm = False
         # V2 running statistics: record = [count, mean[F], M2[F]]; mean=0 / sigma=1 until the first
@@ -76,9 +79,6 @@ class ArsEngine:
         self.B_local = Bl
         self._out = {"returns": torch.empty(Bl, **f64)}
         self._sim_out = {"returns": torch.empty(Bl, **f64)} if sim_params is not None else None
-        self.rec_len = 2 * self.N_local + 1 + 2 * self.no
-        self._record = torch.zeros(self.rec_len, **f64)
-        self._gathered = torch.zeros(self.world * self.rec_len, **f64)
         self.returns = torch.zeros(2 * self.N, **f64)        # last iteration, all ranks
         self._records = torch.zeros(self.world, 1 + 2 * self.no, **f64)
         self.order = torch.zeros(self.N, dtype=torch.int32, device=self.device)
@@ -88,8 +88,15 @@ class ArsEngine:
             self.mask_local = torch.ones(self.N_local, dtype=torch.int32, device=self.device)
             self.n_pass_local = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.mask = torch.ones(self.N, dtype=torch.int32, device=self.device)
-            self.sim_returns = torch.zeros(Bl, **f64)
+            self.sim_returns = torch.zeros(2 * self.N_local, **f64)
         self.last = None
+        # per-iteration record exchange (one packed record per rank): peer-memory kernel or collective
+        self.layout = RecordLayout(self.N_local, self.no if self.v2 else 0, has_mask=sim_params is not None)
+        self.exchange = RecordExchange(self.layout, group=group, device=self.device, transport=transport,
+                                       distributed=use_dist)
+        # a captured NCCL all-gather next to eager collectives on the same communicator hung (round 1):
+        # only the kernel transports are captured
+        self.use_graph = bool(use_graph) and self.exchange.capturable
         # optional (n_sub, chunk): schedule the real rollouts as sub-batches x time-chunks on several streams
         # (ops.ChunkedRollout) -- pays off when 2 N R / world environments are a mid-size batch
         self._chunked = None
@@ -115,7 +122,7 @@ class ArsEngine:
             rollouts_per_policy=self.R, mean=self.mean if self.v2 else None,
             inv_sigma=self.inv_sigma if self.v2 else None, clip_actions=self.clip,
             stats_pivot=self.pivot if want_stats else None, want_trajectory=want_trajectory,
-            screen=screen, out=out)
+            screen=screen, out=out, kernel=self.rollout_kernel)
 
     def run_iteration(self, deltas=None, want_trajectory=False, update=True):
         """One ARS iteration.  `deltas` ([N, ws] device tensor): use these perturbations instead of
@@ -146,7 +153,7 @@ class ArsEngine:
         dir_mask = None
         if self.sim_params is not None:
             sim = self._rollouts(self.sim_params, self._sim_out, deltas_local, None, False, False, None)
-            sim_ret = sim.returns if R == 1 else ops.reduce_returns(sim.returns, R)
+            sim_ret = sim.returns if R == 1 else ops.reduce_returns(sim.returns, R, out=self.sim_returns)
             self.sim_returns = sim_ret
             ops.screen_mask(sim_ret, self.sim_threshold, self.mask_local, self.n_pass_local)
             dir_mask = self.mask_local
@@ -155,27 +162,26 @@ class ArsEngine:
         self.last = res
         if res.stats_partial is not None and res.stats_partial is not getattr(self._chunked, "stats_partial", None):
             self._out["stats_partial"] = res.stats_partial  # reuse: iterations allocate nothing
-        rec = self._record
-        if R == 1:
-            rec[:2 * Nl].copy_(res.returns)
+        # statistics count: every state of every rolled-out environment; in safe mode only the directions
+        # that survived screening were rolled out (device-side count)
+        units = self.n_pass_local if (self.v2 and dir_mask is not None) else None
+        samples = (float(2 * R * self.H) if units is not None else res.samples) if self.v2 else 0.0
+        pack = dict(returns_local=res.returns, n_local=Nl, R=R, mask_local=dir_mask,
+                    stats_partial=res.stats_partial if self.v2 else None, samples=samples, units=units,
+                    pivot=self.pivot if self.v2 else None, n_features=self.layout.n_features)
+        out = dict(returns_all=self.returns, mask_all=self.mask, records=self._records if self.v2 else None)
+        ex = self.exchange
+        if ex.transport in ("local", "p2p"):
+            ops.pack_exchange(ex.handle, **pack, **out)           # one launch: pack, peer stores + flags, unpack
         else:
-            ops.reduce_returns(res.returns, R, out=rec[:2 * Nl])
-        if self.v2:
-            units = self.n_pass_local if dir_mask is not None else None
-            samples = float(2 * R * self.H) if units is not None else res.samples
-            ops.stats_finalize(res.stats_partial, samples, self.pivot, out=rec[2 * Nl:], units=units)
-        if self.world > 1:
-            dist.all_gather_into_tensor(self._gathered, rec, group=self.group)
-            g = self._gathered.view(self.world, self.rec_len)
-            self.returns.view(self.world, 2 * Nl).copy_(g[:, :2 * Nl])
-            self._records.copy_(g[:, 2 * Nl:])
-            if self.mask is not None:
-                self.mask.copy_((~torch.isnan(self.returns.view(self.N, 2)[:, 0])).to(torch.int32))
-        else:
-            self.returns.copy_(rec[:2 * Nl])
-            self._records[0].copy_(rec[2 * Nl:])
-            if self.mask is not None:
-                self.mask.copy_(self.mask_local)
+            # collective fallback: pack kernel, torch.distributed all-gather, torch unpack (eager only)
+            ops.pack_exchange(None, **pack, record_out=ex.record, gathered_world=self.world)
+            returns, mask, records = ex.gather_split(ex.record)
+            self.returns.copy_(returns)
+            if mask is not None:
+                self.mask.copy_(mask)
+            if records is not None:
+                self._records.copy_(records)
         if update:
             self._enqueue_update(deltas)
         return self.returns
@@ -200,6 +206,13 @@ class ArsEngine:
             ops.record_nanmean(self.returns, self.curve, self.iter_dev)
         ops.counter_add(self.iter_dev, 1)
 
+    def check_exchange(self):
+        """Raises if a peer failed to deliver its record in time (sticky device status); synchronises."""
+        epoch, status = self.exchange.status()
+        if status:
+            raise _lib.SwimmerLibError("record exchange timed out waiting for rank %d (epoch %d)" % (status - 1, epoch))
+        return epoch
+
     # ---- host views ----
     def policy_numpy(self):
         n = self.params.n
@@ -210,15 +223,22 @@ class ArsEngine:
 
     def state_dict(self):
         """Everything needed to resume bit-exactly: policy, Philox position, V2 statistics."""
-        return {"W": self.W.cpu().numpy(), "iteration": self.iteration, "seed": self.seed,
-                "stats": self.stats.cpu().numpy(), "mean": self.mean.cpu().numpy(),
-                "inv_sigma": self.inv_sigma.cpu().numpy()}
+        sd = {"W": self.W.cpu().numpy(), "iteration": self.iteration, "seed": self.seed,
+              "stats": self.stats.cpu().numpy(), "mean": self.mean.cpu().numpy(),
+              "inv_sigma": self.inv_sigma.cpu().numpy()}
+        if self.curve is not None:
+            sd["curve"] = self.curve.cpu().numpy()
+        return sd
 
     def load_state_dict(self, sd):
         self.W.copy_(torch.as_tensor(sd["W"]))
-        if int(sd["seed"]) != self.seed and self._graph is not None:
-            self._graph = None  # the seed is a frozen kernel argument of the captured graph
+        if int(sd["seed"]) != self.seed:
+            self._graph = None  # the seed is a frozen kernel argument of the captured graph ...
+            if self._chunked is not None:
+                self._chunked.kw["seed"] = int(sd["seed"])  # ... and of the chunked rollout schedule
         self.iteration, self.seed = int(sd["iteration"]), int(sd["seed"])
+        if self.curve is not None and "curve" in sd:
+            self.curve.copy_(torch.as_tensor(sd["curve"]))
         self.iter_dev.fill_(self.iteration)
         self.stats.copy_(torch.as_tensor(sd["stats"]))
         self.mean.copy_(torch.as_tensor(sd["mean"]))

@@ -14,7 +14,7 @@ from ._lib import (ARS_AGENT, ARS_RLGLUE, ARS_TOPB, DELTA_01, DELTA_PM1, GYM, PO
                    POLICY_EXPLICIT, POLICY_FIXED_ACTION, POLICY_PHILOX, RLGLUE)
 
 __all__ = ["step_batched", "step_batched_models", "accelerations_batched", "rollout", "RolloutResult", "ChunkedRollout", "plan_chunks", "philox_deltas",
-           "ars_topb", "ars_update", "counter_add", "record_nanmean", "stats_finalize", "stats_merge", "reduce_returns", "screen_mask", "policy_actions", "update_args",
+           "ars_topb", "ars_update", "pack_exchange", "counter_add", "record_nanmean", "stats_finalize", "stats_merge", "reduce_returns", "screen_mask", "policy_actions", "update_args",
            "fp64_probe", "obs_dim", "act_dim", "policy_size", "reset_state", "lane_split_envs_per_warp"]
 
 
@@ -481,6 +481,27 @@ def stats_merge(running, records, mean_out=None, inv_sigma_out=None):
                                               F, _lib.ptr(mean_out), _lib.ptr(inv_sigma_out),
                                               _lib.stream_ptr()))
     return running
+
+
+def pack_exchange(handle, *, returns_local=None, n_local, R=1, mask_local=None, stats_partial=None, samples=0.0,
+                  units=None, pivot=None, n_features=0, returns_all=None, mask_all=None, records=None,
+                  record_out=None, gathered_in=None, gathered_world=0):
+    """One launch of swm_ars_pack_exchange (include/swimmer_ars.h): packs this rank's record from the rollout
+    outputs, exchanges it over NVLink peer memory when `handle` (swm_exchange_t*) spans several ranks, and
+    unpacks returns_all / mask_all / records.  handle None + gathered_in: unpack a collective's result;
+    handle None + record_out + gathered_world > 1: pack only."""
+    p = _lib.SwmPack()
+    ref = returns_all if returns_all is not None else record_out
+    p.returns_local, p.n_local, p.rollouts_per_policy = _lib.ptr(returns_local), int(n_local), int(R)
+    p.mask_local = _lib.ptr(mask_local)
+    if stats_partial is not None:
+        p.stats_partial, p.n_blocks = _lib.ptr(stats_partial), stats_partial.shape[0]
+    p.n_features, p.gathered_world, p.samples = int(n_features), int(gathered_world), float(samples)
+    p.units, p.pivot = _lib.ptr(units), _lib.ptr(pivot)
+    p.returns_all, p.mask_all, p.records = _lib.ptr(returns_all), _lib.ptr(mask_all), _lib.ptr(records)
+    p.record_out, p.gathered_in = _lib.ptr(record_out), _lib.ptr(gathered_in)
+    with torch.cuda.device(ref.device):
+        _lib.check(_lib.lib().swm_ars_pack_exchange(handle, ctypes.byref(p), _lib.stream_ptr()))
 
 
 def reduce_returns(returns, R, out=None):

@@ -46,6 +46,11 @@ class Basic_ARS:
     def _t(self, a, dev):
         return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
 
+    def _device(self):
+        """Device of the environment this agent last trained on, else the current CUDA device."""
+        eng = getattr(self, "engine", None)
+        return eng.device if eng is not None else torch.device("cuda", torch.cuda.current_device())
+
     def rollout(self, real_env, policy, H, render=False):
         """-> (R, states[H][2n+2]) like safe_ars/ars.py:13-35 (post-step observations)."""
         res = real_env.rollout_batched(H, policies=np.asarray(policy, dtype=np.float64)[None],
@@ -54,18 +59,19 @@ class Basic_ARS:
         return float(res.returns.cpu()[0]), res.trajectory[:, 0, :].cpu().numpy().tolist()
 
     def sort_directions(self, deltas, rewards):
-        r = self._t(np.asarray(rewards, dtype=np.float64)[:2 * len(deltas)], "cuda")
+        r = self._t(np.asarray(rewards, dtype=np.float64)[:2 * len(deltas)], self._device())
         return ops.ars_topb(r).cpu().tolist()
 
     def update_policy(self, deltas, returns, order, alpha):
         """policy += alpha/(len(order) sigma_R) sum_{i in order} (r+ - r-) delta_i
         (safe_ars/ars.py:48-65); self.policy is a host array as in the reference."""
         N = len(deltas)
-        W = self._t(self.policy, "cuda").reshape(-1)
-        ops.ars_update(W, self._t(np.asarray(returns)[:2 * N], "cuda"), N,
-                       order=torch.as_tensor(np.asarray(order, dtype=np.int32)).cuda(),
+        dev = self._device()
+        W = self._t(self.policy, dev).reshape(-1)
+        ops.ars_update(W, self._t(np.asarray(returns)[:2 * N], dev), N,
+                       order=torch.as_tensor(np.asarray(order, dtype=np.int32)).to(dev),
                        n_order=len(order), divisor=0.0, ddof=0, alpha=alpha,
-                       deltas=self._t(np.asarray(deltas).reshape(N, -1), "cuda"))
+                       deltas=self._t(np.asarray(deltas).reshape(N, -1), dev))
         self.policy = W.cpu().numpy().reshape(np.asarray(self.policy).shape)
 
     def train(self, n_iter, real_env, N, b, alpha, nu, H, return_states=True, seed=0):

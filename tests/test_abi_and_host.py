@@ -117,24 +117,28 @@ def _dist_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import sys
     sys.path.insert(0, ROOT)
-    import swimmer_ars_b200 as S
+    import swimmer_ars_b200 as S  # noqa: F401
     from swimmer_ars_b200 import distributed as D
     dist.init_process_group("gloo", rank=rank, world_size=world)
     N, F = 8, 4
     lo, hi = D.shard_directions(N, rank, world)
+    # exactly the objects ArsEngine builds for a sharded V2 engine in safe mode, on the collective transport
+    layout = D.RecordLayout(hi - lo, n_features=F, has_mask=True)
+    ex = D.RecordExchange(layout, device="cpu", transport="collective", use_cuda=False)
     local = torch.arange(2 * lo, 2 * hi, dtype=torch.float64)          # returns of my directions
+    mask = torch.tensor([(k + rank) % 2 for k in range(hi - lo)], dtype=torch.int32)
     rec = torch.cat([torch.tensor([float(rank + 1)]), torch.full((F,), float(rank)), torch.full((F,), 10. * rank)])
-    packed = D.pack_record(local, rec)
-    out = torch.zeros(world * packed.numel(), dtype=torch.float64)
-    dist.all_gather_into_tensor(out, packed)
-    returns, records = D.unpack_records(out, world, 2 * (hi - lo), F)
-    q.put((rank, returns.tolist(), records.tolist()))
+    ex.record.copy_(layout.pack(local, mask, rec))
+    returns, mask_all, records = ex.gather_split(ex.record)
+    q.put((rank, ex.transport, ex.capturable, returns.tolist(), mask_all.tolist(), records.tolist()))
     dist.destroy_process_group()
 
 
-def test_sharding_and_packed_allgather_gloo(S):
-    """world_size 2 on CPU (gloo): the packed per-rank record round-trips through one all-gather
-    and every rank reconstructs the same 2N returns in direction order + the records in rank order."""
+def test_sharded_record_exchange_gloo(S):
+    """world_size 2 on CPU (gloo): the engine's record exchange on its collective transport
+    (distributed.RecordLayout / RecordExchange, the code ArsEngine._enqueue runs when peer memory is
+    unavailable): every rank reconstructs the same 2N returns in direction order, the screening mask and
+    the statistics records in rank order."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -143,13 +147,19 @@ def test_sharding_and_packed_allgather_gloo(S):
     [p.start() for p in procs]
     got = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(60) for p in procs]
-    for rank, returns, records in got:
+    for rank, transport, capturable, returns, mask_all, records in got:
+        assert transport == "collective" and capturable is False
         assert returns == [float(i) for i in range(16)]
+        assert mask_all == [0, 1, 0, 1, 1, 0, 1, 0]
         assert records[0][0] == 1.0 and records[1][0] == 2.0 and records[1][1] == 1.0 and records[1][-1] == 10.0
     from swimmer_ars_b200 import distributed as D
     assert D.shard_directions(1024, 3, 8) == (384, 512)
     with pytest.raises(ValueError):
         D.shard_directions(10, 0, 4)
+    lay = D.RecordLayout(128, n_features=12, has_mask=False)
+    assert (lay.returns, lay.mask, lay.stats, lay.length) == ((0, 256), (256, 256), (256, 281), 281)
+    assert lay.length == S._lib.lib().swm_pack_record_doubles(128, 0, 12)
+    assert D.RecordLayout(4, 0, True).length == S._lib.lib().swm_pack_record_doubles(4, 1, 0) == 12
 
 
 def test_chunk_plan_partition(S):

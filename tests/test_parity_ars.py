@@ -395,3 +395,76 @@ def test_engine_with_chunked_rollouts_matches_plain_engine(S, mode):
         np.testing.assert_allclose(chunked.inv_sigma.cpu().numpy(), plain.inv_sigma.cpu().numpy(), rtol=1e-9)
         assert torch.equal(chunked.W, graphed.W) and torch.equal(chunked.stats, graphed.stats)
     assert graphed._graph is not None
+
+
+@pytest.mark.parametrize("R,with_mask,v2", [(1, False, True), (3, True, True), (2, False, False)])
+def test_pack_exchange_kernel_matches_separate_kernels(S, R, with_mask, v2):
+    """swm_ars_pack_exchange (one launch: per-direction mean returns, screening mask, V2 moment record, unpack)
+    against the separate kernels it replaces (swm_reduce_returns + swm_stats_finalize), and its collective
+    fallback (record_out -> all-gather -> gathered_in) against distributed.RecordLayout.split."""
+    from swimmer_ars_b200 import distributed as D
+    n, Nl, H = 5, 7, 60
+    no = 2 * n + 2
+    p = S.make_params(n=n)
+    rng = np.random.default_rng(R)
+    W = torch.as_tensor(rng.uniform(-1, 1, (n - 1) * no) * 0.1).cuda()
+    mask = torch.tensor([1, 0, 1, 1, 1, 0, 1], dtype=torch.int32, device="cuda") if with_mask else None
+    piv = S.ops.reset_state(n)
+    mean, inv = torch.zeros(no, dtype=torch.float64, device="cuda"), torch.ones(no, dtype=torch.float64, device="cuda")
+    res = S.ops.rollout(p, H, B=2 * Nl * R, base_policy=W, nu=0.05, seed=3, rollouts_per_policy=R, dir_mask=mask,
+                        mean=mean if v2 else None, inv_sigma=inv if v2 else None, stats_pivot=piv if v2 else None)
+    F = no if v2 else 0
+    f64 = dict(dtype=torch.float64, device="cuda")
+    returns_all, records = torch.zeros(2 * Nl, **f64), torch.zeros(1, 1 + 2 * no, **f64)
+    mask_all = torch.zeros(Nl, dtype=torch.int32, device="cuda") if with_mask else None
+    units = torch.tensor([int(mask.sum())], dtype=torch.int32, device="cuda") if with_mask else None
+    samples = float(2 * R * H) if with_mask else (res.samples if v2 else 0.0)
+    pack = dict(returns_local=res.returns, n_local=Nl, R=R, mask_local=mask, stats_partial=res.stats_partial,
+                samples=samples, units=units, pivot=piv if v2 else None, n_features=F)
+    S.ops.pack_exchange(None, **pack, returns_all=returns_all, mask_all=mask_all, records=records if v2 else None)
+    want_r = S.ops.reduce_returns(res.returns, R) if R > 1 else res.returns
+    assert torch.equal(torch.nan_to_num(returns_all), torch.nan_to_num(want_r))
+    assert torch.equal(torch.isnan(returns_all), torch.isnan(want_r))
+    if with_mask:
+        assert torch.equal(mask_all, mask)
+    if v2:
+        want_rec = S.ops.stats_finalize(res.stats_partial, samples, piv, units=units)
+        np.testing.assert_allclose(records[0].cpu().numpy(), want_rec.cpu().numpy(), rtol=1e-12, atol=1e-13)
+    # collective fallback: pack only, a pretend all-gather over 3 ranks, unpack by the kernel and by torch
+    lay = D.RecordLayout(Nl, F, with_mask)
+    rec = torch.zeros(lay.length, **f64)
+    S.ops.pack_exchange(None, **pack, record_out=rec, gathered_world=3)
+    gathered = torch.cat([rec, rec * 2.0, rec * 3.0])
+    ra, rc = torch.zeros(3 * 2 * Nl, **f64), torch.zeros(3, 1 + 2 * no, **f64)
+    ma = torch.zeros(3 * Nl, dtype=torch.int32, device="cuda") if with_mask else None
+    S.ops.pack_exchange(None, n_local=Nl, n_features=F, mask_local=mask, gathered_in=gathered, gathered_world=3,
+                        returns_all=ra, mask_all=ma, records=rc if v2 else None)
+    t_r, t_m, t_rec = lay.split(gathered, 3)
+    assert torch.equal(torch.nan_to_num(ra), torch.nan_to_num(t_r))
+    if with_mask:
+        assert torch.equal(ma, t_m)
+    if v2:
+        assert torch.equal(rc[:, :1 + 2 * F], t_rec)
+
+
+def test_v2_safe_engine_with_everything_screened_out_keeps_identity_normalisation(S):
+    """ars_agent.py:179-182 recomputes mean / cov only `if len(rewards) > 0`: an iteration whose directions
+    are all screened out (threshold above every simulated return) must leave W, mean = 0 and sigma = 1
+    untouched instead of dividing by a zero count."""
+    n = 3
+    p, sim = S.make_params(n=n), S.make_params(n=n, l_i=1.001)
+    eng = S.ArsEngine(p, N=6, b=6, alpha=0.02, nu=0.03, H=50, v2=True, seed=1, distributed=False,
+                      sim_params=sim, sim_threshold=1e9)
+    for _ in range(2):
+        r = eng.run_iteration()
+        assert bool(torch.isnan(r).all())
+    assert float(eng.W.abs().max()) == 0.0
+    assert torch.equal(eng.mean, torch.zeros_like(eng.mean)) and torch.equal(eng.inv_sigma, torch.ones_like(eng.inv_sigma))
+    assert float(eng.stats[0]) == 0.0
+    eng.sim_threshold = -1e9   # now everything passes: statistics start from this iteration
+    r = eng.run_iteration()
+    assert bool(torch.isfinite(r).all()) and float(eng.stats[0]) == 12 * 50
+    assert bool(torch.isfinite(eng.inv_sigma).all()) and float(eng.W.abs().max()) > 0.0
+    # a NaN simulator return is screened out (declared deviation from the reference's `<=`)
+    m, cnt = S.ops.screen_mask(torch.tensor([1.0, float("nan"), 1.0, 2.0], dtype=torch.float64, device="cuda"), 0.0)
+    assert m.tolist() == [0, 1] and int(cnt) == 1

@@ -37,7 +37,7 @@ def main():
         inv = torch.ones_like(mean)
         piv = S.ops.reset_state(n)
         print("n=%d  V2 + moments, Philox policies, H=%d" % (n, H))
-        for B in (64, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768):
+        for B in [int(x) for x in os.environ.get("SWEEP_B", "64,256,512,1024,2048,4096,8192,16384,32768").split(",")]:
             row = []
             for kern in (S.KERNEL_THREAD, S.KERNEL_LANES):
                 out = {}
