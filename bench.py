@@ -1,11 +1,15 @@
-"""bench.py -- swimmer env-steps/s on BASELINE.json config[1] (isolated batched physics: 3-segment
-swimmer, 65,536 envs per GPU, fixed random actions, 1,000 explicit-Euler steps), plus the ARS
-iteration rate of config[2] as a supplementary key.
+"""bench.py -- the metric of BASELINE.json: swimmer env-steps/s and ARS iterations/s on 1/2/4/8 B200, % FP64 peak.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--no-ars] [--no-cpu]
 
-A "step" is one pass of the fused rollout kernel over one batch (65,536 envs x 1,000 steps =
-65.5 M env-steps per GPU).  Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement".
+The driver-parsed headline (`metric`, `value`, `e2e`, `roofline`) is BASELINE config[1] (isolated batched
+physics: 3-segment swimmer, 65,536 envs per GPU, fixed random actions, 1,000 explicit-Euler steps; a "step"
+is one pass of the fused rollout over one batch = 65.5 M env-steps per GPU).  The same JSON line carries, as
+first-class keys under `ars`, the ARS iterations/s of BASELINE config[2] (V2, n = 5, 1,024 directions),
+config[3] (safe exploration, n = 3, 256 directions, simulator screening then real rollouts) and config[4]
+(n = 10, 4,096 directions x 2 x 128 rollouts), each sharded over the N GPUs, with their parity against an
+unsharded engine, plus a >= 2 s sustained run and the CPU legs.  Prints ONE JSON line (rank 0).
+See DESIGN.md section "Measurement".
 """
 import argparse
 import json
@@ -23,11 +27,14 @@ sys.path.insert(0, ROOT)
 N_SEG, B_PER_GPU, H = 3, 65536, 1000
 W_REF = {3: 822, 5: 1751, 10: 5701}        # algorithmic flops per env-step
 W_REF_V2 = {3: 838, 5: 1775, 10: 5745}
-# Measured once per kernel change with ncu (profiles/r01c_summary.md), config[1] kernel, per launch:
-NCU_DRAM_BYTES_PER_LAUNCH = 1.07e6          # dram__bytes_read.sum + dram__bytes_write.sum
-NCU_EXEC_FLOPS_PER_ENV_STEP = 312.0         # executed FP64 flops per env-step: 2 per DFMA, 1 per DADD/DMUL (ncu source page)
+# Measured once per kernel change with ncu (profiles/r01c_summary.md, profiles/r02_summary.md):
+NCU_DRAM_BYTES_PER_LAUNCH = 1.07e6          # config[1] kernel: dram__bytes_read.sum + dram__bytes_write.sum
+# FP64 flops one environment step costs in the one-thread-per-environment kernels (2 per DFMA, 1 per DADD/DMUL,
+# ncu source-page instruction counts / 32 lanes): the non-redundant work of a step
+EXEC_FLOPS = {"n3_fixed": 312.0, "n3_v1": 344.0, "n5_v2": 735.0, "n10_v2": 1800.0}
 METRIC, UNIT = "swimmer env-steps/sec", "env-steps/s"
 WORKLOAD = "config[1]: 3-segment swimmer, 65,536 envs per GPU, fixed random actions U(-5,5), 1,000 explicit-Euler steps"
+CONFIG = {"workload": WORKLOAD, "n_segments": N_SEG, "envs_per_gpu": B_PER_GPU, "H": H}  # identical on both arms
 
 
 def parse():
@@ -36,14 +43,24 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-ars", action="store_true", help="skip the supplementary ARS-iteration measurement")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ars", action="store_true", help="skip the ARS-iteration measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained run")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU legs (oracle port, all host threads).  The only place bench.py executes oracle/.
+# CPU legs.  The only place bench.py executes oracle/ (the C port of the reference, all host threads) and
+# baseline/_ref (the unmodified Python reference, staged by oracle/stage_reference.py).
 # ----------------------------------------------------------------------------------------------
+def _threads_run(work, threads):
+    t0 = time.perf_counter()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return time.perf_counter() - t0
+
+
 def cpu_fixed_action_rate(n_envs, steps, threads):
     """env-steps/s of the C port of the reference dynamics on `threads` host threads."""
     from oracle import oracle_lib as O
@@ -51,16 +68,10 @@ def cpu_fixed_action_rate(n_envs, steps, threads):
     actions = np.random.default_rng(0).uniform(-5, 5, (n_envs, N_SEG - 1))
     O.lib()
     bounds = np.linspace(0, n_envs, threads + 1).astype(int)
-    out = [None] * threads
 
     def work(i):
-        out[i] = O.rollout_fixed_batch(p, O.GYM, actions, steps, int(bounds[i]), int(bounds[i + 1]),
-                                       want_final=False)[0]
-    t0 = time.perf_counter()
-    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
-    [t.start() for t in ts]
-    [t.join() for t in ts]
-    dt = time.perf_counter() - t0
+        O.rollout_fixed_batch(p, O.GYM, actions, steps, int(bounds[i]), int(bounds[i + 1]), want_final=False)
+    dt = _threads_run(work, threads)
     return n_envs * steps / dt, dt
 
 
@@ -68,6 +79,86 @@ def cpu_sample_size(threads, target_s):
     rate1, _ = cpu_fixed_action_rate(64, 200, 1)   # calibration: ~12.8k steps on one thread
     envs = int(max(threads, min(B_PER_GPU, rate1 * threads * target_s / H)))
     return max(threads, (envs // threads) * threads)
+
+
+def cpu_ars_iteration(n, N_dirs, v2, threads, target_s=6.0, safe=False):
+    """One ARS iteration of the C port (linear-policy rollouts on all host threads + numpy ranking / update) on
+    a bounded sample of the N directions; the iteration rate is extrapolated from the sample's rollout rate
+    (the update is < 1 % of an iteration).  safe: every direction also costs two simulator rollouts."""
+    from oracle import oracle_lib as O
+    p = O.make_params(n=n)
+    no, ws = 2 * n + 2, (n - 1) * (2 * n + 2)
+    rng = np.random.default_rng(1)
+    W = rng.uniform(-1, 1, ws) * 0.05
+    mean, inv = (np.zeros(no), np.ones(no)) if v2 else (None, None)
+    O.lib()
+
+    def run(dirs):
+        d = 2 * rng.random((dirs, ws)) - 1
+        pol = np.stack([W + s * 0.01 * d[k] for k in range(dirs) for s in (1, -1)])
+        bounds = np.linspace(0, 2 * dirs, threads + 1).astype(int)
+        out = [None] * threads
+
+        def work(i):
+            out[i] = O.rollout_policy_batch(p, O.GYM, pol, H, mean, inv, int(bounds[i]), int(bounds[i + 1]))
+        dt = _threads_run(work, threads)
+        rets = np.sum(out, axis=0)
+        O.update_policy(W, d, rets, b=dirs, alpha=0.0075, semantics=0)
+        return dt
+    t_probe = run(threads)                                   # 2 rollouts per thread
+    per_dir = t_probe / threads
+    dirs = int(max(threads, min(N_dirs, target_s / per_dir)))
+    t = run(dirs)
+    rollouts_per_dir = 4 if safe else 2
+    iter_s = t / dirs * N_dirs * (rollouts_per_dir / 2)
+    return {"iters_per_s": 1.0 / iter_s, "env_steps_per_s": N_dirs * rollouts_per_dir * H / iter_s, "cores": threads,
+            "kind": "port", "sample": "%d of %d directions (x2 rollouts x %d steps) in %.1f s, extrapolated" % (dirs, N_dirs, H, t)}
+
+
+def python_reference_legs(threads, procs_iters=1):
+    """The UNMODIFIED Python reference (baseline/_ref, staged from the reference tree): BASELINE config[0] =
+    ARSAgent(seed=0).runOneIteration() with n = 3, V1, N = 8, H = 1000 on one core, and one such agent per
+    host core (the reference's own parallelism: one Ray actor per seed, ars/experiment.py:64-72)."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref_root, "ars", "ars_agent.py")):
+        return {"unavailable": "baseline/_ref not staged (run __graft_entry__.build() where /root/reference exists)"}
+    code = (
+        "import sys, time, os\n"
+        "os.environ['SWIMMER_REFERENCE_ROOT'] = %r\n"
+        "sys.path.insert(0, %r)\n"
+        "from oracle import ref_harness as R\n"
+        "ns = R.load()\n"
+        "ep = ns.EnvParam('x', n=3, H=1000, l_i=1., m_i=1., h=1e-3, k=10., epsilon=0)\n"
+        "ap = ns.ARSParam('a', V1=True, n_iter=1, H=1000, N=8, b=8, alpha=0.0075, nu=0.01, safe=False, threshold=0, initial_w='Zero')\n"
+        "ag = ns.ARSAgent(ep, ap, seed=int(sys.argv[1]))\n"
+        "t = time.perf_counter(); r = ag.runOneIteration(); dt = time.perf_counter() - t\n"
+        "print('RESULT', dt, float(r[0]), float(r[1]))\n" % (ref_root, ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+
+    def launch(seed):
+        return subprocess.Popen([sys.executable, "-c", code, str(seed)], stdout=subprocess.PIPE,
+                                stderr=subprocess.DEVNULL, text=True, env=env)
+
+    def result(pr):
+        out = pr.communicate(timeout=300)[0]
+        for ln in out.splitlines():
+            if ln.startswith("RESULT"):
+                _, dt, r0, r1 = ln.split()
+                return float(dt), float(r0), float(r1)
+        raise RuntimeError("python reference leg failed: " + out[-500:])
+    dt1, r0, r1 = result(launch(0))
+    # survey-recorded returns of config[0], seed 0, iteration 0 (SURVEY 8c): proves it is the reference that ran
+    ok = abs(r0 - (-0.11878042019245531)) < 1e-12 and abs(r1 - 0.46055543070364563) < 1e-12
+    t0 = time.perf_counter()
+    prs = [launch(s) for s in range(threads)]
+    dts = [result(pr)[0] for pr in prs]
+    wall = time.perf_counter() - t0
+    return {"kind": "reference", "workload": "config[0]: ARS V1, 3-segment swimmer, 8 directions, H=1000 (ars/ars_agent.py runOneIteration, numpy)",
+            "one_core": {"iters_per_s": 1.0 / dt1, "env_steps_per_s": 16 * H / dt1, "cores": 1},
+            "all_cores": {"agent_iters_per_s": threads / wall, "env_steps_per_s": threads * 16 * H / wall, "cores": threads,
+                          "note": "one agent (seed) per core, one iteration each, process start-up included in the wall time; "
+                                  "mean in-process iteration time %.2f s" % float(np.mean(dts))},
+            "returns_match_survey": bool(ok)}
 
 
 def ref_cpp_rate(steps=20000):
@@ -106,14 +197,18 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "data": "synthetic", "config": dict(CONFIG),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "C port of the reference gym swimmer (oracle/swimmer_oracle.c, dense (n+2) formulation of "
-                "remy_swimmer_env.py) -- the Python reference itself cannot travel to the GPU box; it ran at "
-                "~5.5k env-steps/s/core in the build container (BASELINE.md section 2)",
+        "note": "value = C port of the reference gym swimmer (oracle/swimmer_oracle.c, the dense (n+2) formulation of "
+                "remy_swimmer_env.py) on all host threads: ~270x faster per core than the reference's own numpy code, "
+                "i.e. the conservative baseline; the unmodified Python reference is timed beside it (python_reference)",
     }
+    if not args.no_cpu:
+        line["python_reference"] = python_reference_legs(threads)
+        line["ars_cpu"] = {"config[2]": cpu_ars_iteration(5, 1024, True, threads),
+                           "config[3]": cpu_ars_iteration(3, 256, False, threads, target_s=3.0, safe=True)}
     cpp = ref_cpp_rate()
     if cpp:
         line["ref_cpp_rlglue_1core"] = {"value": cpp, "unit": UNIT, "kind": "reference",
@@ -143,7 +238,27 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.rows.append(ln.strip())
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def window(self, t0, t1):
+        """Samples taken in [t0, t1] (perf_counter): median SM clock, median / max power, throttle reasons."""
+        sm, pw, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, r in list(self.rows):
+            if t < t0 or t > t1:
+                continue
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); pw.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz_median": float(np.median(sm)) if sm else None, "power_w_median": float(np.median(pw)) if pw else None,
+                "power_w_max": float(np.max(pw)) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
     def stop(self):
         if self.proc is None:
@@ -155,7 +270,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for _, r in self.rows:
             c = [x.strip() for x in r.split(",")]
             if len(c) < 7:
                 continue
@@ -170,8 +285,8 @@ class ClockSampler:
         hot = sorted(sm)[len(sm) // 2:] if sm else []
         return {"sm_mhz": float(np.median(hot)) if hot else None, "sm_max_mhz": mx,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "note": "nvidia-smi -lms 100 from before warm-up to the end of the e2e region, same kernel "
-                        "kept running until >=5 samples; median of the upper half of samples"}
+                "note": "nvidia-smi -lms 100 from before warm-up to the end of the sustained run; median of the "
+                        "upper half of samples (the lower half contains idle gaps between the measured regions)"}
 
 
 def run_b200(args):
@@ -197,6 +312,12 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.cpu()[0])
 
     def single_launch():
         return S.ops.rollout(params, H, actions=actions, want_final=True, out=out)
@@ -249,8 +370,7 @@ def run_b200(args):
         evs.append((e0, e1))
     barrier()
     wall = time.perf_counter() - t_wall0
-    ms = [a.elapsed_time(b) for a, b in evs]
-    t_dev = torch.tensor([sum(ms)], dtype=torch.float64, device=device)
+    t_dev_s = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)) * 1e-3
     # ---- supplementary: one plain swm_rollout launch per step (no chunking), same timing method ----
     evs1 = []
     for _ in range(args.steps):
@@ -261,7 +381,7 @@ def run_b200(args):
         e1.record(stream)
         evs1.append((e0, e1))
     barrier()
-    t_single = torch.tensor([sum(a.elapsed_time(b) for a, b in evs1)], dtype=torch.float64, device=device)
+    t_single_s = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs1)) * 1e-3
 
     # ---- supplementary: the same K launches with TWO in flight (two streams, device-resident inputs, no
     # flush).  One config[1] batch is only 3.46 warps per SM sub-partition; two batches fill the FP64 pipe. ----
@@ -280,7 +400,7 @@ def run_b200(args):
         stream.wait_stream(st)
     c1.record(stream)
     barrier()
-    t_conc = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=device)
+    t_conc_s = max_over_ranks(c0.elapsed_time(c1)) * 1e-3
 
     # ---- end-to-end through the host-buffer entry point: every step uploads its actions from pinned host
     # memory and downloads returns + final states into pinned host memory (SwimmerEnv.rollout_batched_host,
@@ -303,119 +423,83 @@ def run_b200(args):
     env.synchronize_host()
     e1.record(stream)
     barrier()
-    t_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    t_e2e_s = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
     e2e_check = float(host_ret[(args.steps - 1) & 1].sum())  # the host really holds the results
     assert np.isfinite(e2e_check)
-    # nvidia-smi needs ~100 ms per sample: if the timed regions above were too short to be sampled,
-    # keep the same kernel running (untimed) until a few samples under load exist.
-    if sampler:
-        t_end = time.perf_counter() + 3.0
-        n0 = len(sampler.rows)
-        while len(sampler.rows) < n0 + 5 and time.perf_counter() < t_end:
-            for _ in range(20):
-                one_step()
-            torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t_conc, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t_single, op=dist.ReduceOp.MAX)
-    t_dev_s, t_e2e_s = float(t_dev.cpu()[0]) * 1e-3, float(t_e2e.cpu()[0]) * 1e-3
+
     total_steps = float(world) * B_PER_GPU * H * args.steps
     value = total_steps / t_dev_s
     e2e_value = total_steps / t_e2e_s
-    conc_value = total_steps / (float(t_conc.cpu()[0]) * 1e-3)
-    single_value = total_steps / (float(t_single.cpu()[0]) * 1e-3)
+    conc_value = total_steps / t_conc_s
+    single_value = total_steps / t_single_s
 
-    # ---- supplementary: ARS iterations/s (rollouts + NCCL exchange + ranking + update) ----
-    #   config[2]: ARS V2, n=5, 1,024 directions, H=1000  (2,048 envs in total: latency-bound)
-    #   config[4]: n=10, 4,096 directions x 2 x 128 rollouts = 1,048,576 envs, H=1000 (throughput-bound)
+    # ---- sustained run: the timed step replayed back to back for >= 2 s (no flush, no host gaps) with the
+    # clock / power samples of exactly that window: the 18 ms headline survives thermals and the power cap ----
+    sustained = None
+    if not args.no_sustained:
+        reps = max(50, int(2.2 / (t_dev_s / args.steps)))
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        s0.record(stream)
+        for _ in range(reps):
+            one_step()
+        s1.record(stream)
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        t_sus = max_over_ranks(s0.elapsed_time(s1)) * 1e-3
+        sustained = {"value": float(world) * B_PER_GPU * H * reps / t_sus, "unit": UNIT, "seconds": t_sus, "steps": reps,
+                     "note": "the same CUDA-graph step replayed back to back (device-resident inputs, no L2 flush between steps)"}
+        if sampler:
+            sustained["clocks"] = sampler.window(w0 + 0.15, w1)
+    clocks = sampler.stop() if sampler else None
+
     ars = None
     if not args.no_ars:
-        ars = []
-        for tag, n_, Ndir, R_, K2, desc in (
-                ("config[2]", 5, 1024, 1, 5, "ARS V2, 5-segment swimmer, 1,024 directions (2,048 rollouts), H=1000"),
-                ("config[4]", 10, 4096, 128, 2, "ARS V2, 10-segment swimmer, 4,096 directions x 2 x 128 rollouts "
-                                                "(1,048,576 envs, reset + 1e-2*U[0,1) starts), H=1000")):
-            if Ndir % world != 0:
-                continue
-            eng = S.ArsEngine(S.make_params(n=n_), N=Ndir, b=Ndir, alpha=0.0075, nu=0.01, H=1000, v2=True,
-                              semantics=S.ARS_AGENT, seed=0, device=device, rollouts_per_direction=R_,
-                              init_perturb=1e-2 if R_ > 1 else 0.0, use_graph=True)
-            for _ in range(3 if R_ == 1 else 2):  # eager warm-up, graph capture (1 GPU), replay
-                eng.run_iteration()
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(K2):
-                eng.run_iteration()
-            e1.record(stream)
-            barrier()
-            t_ars = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-            if world > 1:
-                dist.all_reduce(t_ars, op=dist.ReduceOp.MAX)
-            t_ars_s = float(t_ars.cpu()[0]) * 1e-3
-            steps_per_iter = 2.0 * Ndir * R_ * 1000
-            ars.append({"workload": "%s: %s; directions sharded over %d GPU(s) (strong scaling)" % (tag, desc, world),
-                        "iters_per_s": K2 / t_ars_s, "env_steps_per_s": K2 * steps_per_iter / t_ars_s,
-                        "ms_per_iter": 1e3 * t_ars_s / K2, "iters_timed": K2,
-                        "roofline_frac_fp64": (K2 * steps_per_iter / t_ars_s / world) * W_REF_V2[n_] / 1e12 / fp64_peak_tflops,
-                        "launch": "CUDA graph replay" if eng._graph is not None else "eager (NCCL exchange)",
-                        "mean_return_last": float(eng.returns.mean().cpu())})
-            del eng
-        if world == 1:
-            # seed fan-out (ars/experiment.py:64-72: one agent per seed): 32 agents of config[0]
-            # (n=3, V1, 8 directions, H=1000), one CUDA stream + one graph launch per agent-iteration
-            seeds, K3 = 32, 20
-            fan = S.SeedFanout(S.make_params(n=3), range(seeds), N=8, b=8, alpha=0.0075, nu=0.01, H=1000, device=device)
-            fan.run(2)
-            barrier()
-            t0 = time.perf_counter()
-            fan.run(K3, include_initial=False)
-            dt = time.perf_counter() - t0
-            ars.append({"workload": "config[0] x %d seeds: ARS V1, 3-segment swimmer, 8 directions, H=1000, one agent per "
-                                    "seed on one GPU (seed fan-out)" % seeds,
-                        "agent_iters_per_s": seeds * K3 / dt, "env_steps_per_s": seeds * K3 * 16 * 1000 / dt,
-                        "ms_per_round": 1e3 * dt / K3, "timing": "host wall clock around %d rounds incl. final sync" % K3})
-            del fan
+        ars = measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_peak_tflops)
 
     if rank == 0:
         cpu = None
+        extra_cpu = {}
         if not args.no_cpu:
             threads = os.cpu_count() or 1
-            envs = cpu_sample_size(threads, 12.0)
+            envs = cpu_sample_size(threads, 10.0)
             rate, dt = cpu_fixed_action_rate(envs, H, threads)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "%d envs x %d steps of the same workload in %.1f s (oracle C port of the "
                              "reference gym swimmer)" % (envs, H, dt)}
+            if world == 1:
+                extra_cpu["ars_cpu"] = {"config[2]": cpu_ars_iteration(5, 1024, True, threads),
+                                        "config[3]": cpu_ars_iteration(3, 256, False, threads, target_s=3.0, safe=True)}
+                extra_cpu["python_reference"] = python_reference_legs(threads)
         ms_per_step = 1e3 * t_dev_s / args.steps
-        achieved = (value / world) * W_REF[N_SEG] / 1e12
+        per_gpu = value / world
+        exec_tf = per_gpu * EXEC_FLOPS["n3_fixed"] / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_segments": N_SEG, "envs_per_gpu": B_PER_GPU, "H": H,
-                       "l2": "flushed between steps (256 MiB write outside the timed events); inputs 1 MiB",
-                       "schedule": "each step = one CUDA-graph launch of %d swm_rollout kernels: 16 sub-batches x "
-                                   "64-step chunks on 16 streams, state chained through final_state -> init_state, "
-                                   "final states bit-identical to a single launch" % plan.launches,
-                       "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak_tflops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+            "config": dict(CONFIG),
+            "run": {"l2": "flushed between steps (256 MiB write outside the timed events); inputs 1 MiB",
+                    "schedule": "each step = one CUDA-graph launch of %d swm_rollout kernels: 16 sub-batches x "
+                                "64-step chunks on 16 streams, state chained through final_state -> init_state, "
+                                "final states bit-identical to a single launch" % plan.launches,
+                    "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
+            "roofline": {"bound": "fp64", "achieved": exec_tf, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+                         "frac": exec_tf / fp64_peak_tflops, "flops_per_env_step": EXEC_FLOPS["n3_fixed"],
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
                                          "profiles/r01c_n3_fixed_ncu.csv): ~0 B per env-step, not HBM-bound",
                          "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 "
                                         "entry; nominal 37.2 TFLOP/s)",
-                         "flops_per_env_step": W_REF[N_SEG],
-                         "executed": {"flops_per_env_step": NCU_EXEC_FLOPS_PER_ENV_STEP,
-                                      "achieved": (value / world) * NCU_EXEC_FLOPS_PER_ENV_STEP / 1e12,
-                                      "frac": (value / world) * NCU_EXEC_FLOPS_PER_ENV_STEP / 1e12 / fp64_peak_tflops,
-                                      "note": "FP64 flops the O(n) kernel really executes (ncu instruction counts) against "
-                                              "the same DFMA peak; on B200 a DFMA with three register sources issues "
-                                              "every 3 cycles, so the pipe saturates below 1.0 (profiles/r01b_summary.md)"},
-                         "note": "achieved = per-GPU env-steps/s x 822 algorithmic flops/env-step of the reference's "
-                                 "dense formulation (SURVEY 8d); the O(n) kernel executes fewer real flops"},
+                         "note": "achieved = per-GPU env-steps/s x 312 FP64 flops the O(n) kernel EXECUTES per env-step "
+                                 "(ncu instruction counts, profiles/r01c_summary.md); a DFMA with three register sources "
+                                 "issues every 3.1 cycles on B200, so the pipe saturates below 1.0",
+                         "algorithmic": {"flops_per_env_step": W_REF[N_SEG], "achieved": per_gpu * W_REF[N_SEG] / 1e12,
+                                         "frac": per_gpu * W_REF[N_SEG] / 1e12 / fp64_peak_tflops,
+                                         "note": "SURVEY 8d accounting: the reference's dense O(n^3) formulation costs "
+                                                 "822 flops per env-step; > 1 because the kernel solves the same "
+                                                 "equations in O(n)"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B_PER_GPU * (N_SEG - 1) * 8,
                     "d2h_bytes_per_step": B_PER_GPU * (2 * N_SEG + 3) * 8,
                     "api": "SwimmerEnv.rollout_batched_host: pinned host actions in, pinned host returns + final states "
@@ -424,20 +508,201 @@ def run_b200(args):
                               "note": "one plain swm_rollout launch per step (the whole batch in one kernel, no "
                                       "chunking), same events / flush as `value`"},
             "two_in_flight": {"value": conc_value, "unit": UNIT, "streams": 2,
-                              "roofline_frac_executed": (conc_value / world) * NCU_EXEC_FLOPS_PER_ENV_STEP / 1e12 / fp64_peak_tflops,
+                              "roofline_frac_executed": (conc_value / world) * EXEC_FLOPS["n3_fixed"] / 1e12 / fp64_peak_tflops,
                               "note": "same kernel, same inputs resident in HBM, K launches alternating on two streams "
                                       "(no L2 flush): one 65,536-env batch is 3.46 warps per SM sub-partition (the busiest "
                                       "holds 4), two batches in flight balance and fill the FP64 pipe; this is also why "
                                       "the double-buffered e2e number exceeds the one-launch-at-a-time `value`"},
+            "sustained": sustained,
             "gpu_launches": args.steps * plan.launches, "clocks": clocks, "cpu_baseline": cpu,
             "wall_s_timed_region": wall,
         }
+        line.update(extra_cpu)
         if ars:
             line["ars"] = ars
+            line["ars_iters_per_s"] = {k: v["iters_per_s"] for k, v in ars.items() if "iters_per_s" in v}
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_peak_tflops):
+    """ARS iterations/s of BASELINE config[2], config[3], config[4]: rollouts + record exchange + ranking +
+    update, directions sharded over the `world` GPUs (strong scaling), one CUDA-graph launch per iteration."""
+    import torch
+    stream = torch.cuda.current_stream()
+    res = {}
+
+    def rel(x, y):
+        x, y = torch.nan_to_num(x), torch.nan_to_num(y)
+        return float(((x - y).abs().max() / y.abs().max().clamp_min(1e-300)).cpu())
+
+    def timed(eng, iters, warm):
+        for _ in range(warm):   # eager warm-up, graph capture, replay
+            eng.run_iteration()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            eng.run_iteration()
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) * 1e-3
+
+    def parity(make, iters=3):
+        """Sharded engine vs an unsharded engine run by rank 0 alone, same seed, `iters` iterations: relative
+        difference of the policy and of the last returns (north-star tolerance 1e-6)."""
+        if world == 1:
+            return None
+        sh = make(True)
+        for _ in range(iters):
+            sh.run_iteration()
+        out = None
+        if rank == 0:
+            single = make(False)
+            for _ in range(iters):
+                single.run_iteration()
+            out = {"iterations": iters, "policy_rel_diff": rel(sh.W, single.W), "returns_rel_diff": rel(sh.returns, single.returns),
+                   "tolerance": 1e-6}
+            out["ok"] = bool(out["policy_rel_diff"] < 1e-6 and out["returns_rel_diff"] < 1e-6)
+            del single
+        sh.exchange.close()
+        barrier()
+        return out
+
+    def describe(eng, kernel_cfg):
+        return {"launch": "CUDA graph replay" if eng._graph is not None else "eager",
+                "exchange": eng.exchange.transport, "rollout_kernel": kernel_cfg}
+
+    # ---------------- config[2]: ARS V2, n = 5, 1,024 directions ----------------
+    if 1024 % world == 0:
+        def make2(sharded):
+            return S.ArsEngine(S.make_params(n=5), N=1024, b=1024, alpha=0.0075, nu=0.01, H=1000, v2=True,
+                               semantics=S.ARS_AGENT, seed=0, device=device, use_graph=True,
+                               distributed=None if sharded else False)
+        par = parity(make2)
+        eng = make2(True)
+        K = 20
+        t = timed(eng, K, 5)
+        steps = 2.0 * 1024 * 1000
+        ee = eng.check_exchange()
+        res["config[2]"] = dict(
+            workload="config[2]: ARS V2 (obs normalisation), 5-segment swimmer, 1,024 directions (2,048 rollouts), H=1000; "
+                     "directions sharded over %d GPU(s) (strong scaling)" % world,
+            iters_per_s=K / t, ms_per_iter=1e3 * t / K, env_steps_per_s=K * steps / t, iters_timed=K,
+            mean_return_last=float(eng.returns.mean().cpu()), exchange_epochs=ee, parity_vs_single=par,
+            roofline={"bound": "latency (2,048 envs: one lane-split warp per SM sub-partition)",
+                      "executed": {"flops_per_env_step": EXEC_FLOPS["n5_v2"],
+                                   "frac": (K * steps / t / world) * EXEC_FLOPS["n5_v2"] / 1e12 / fp64_peak_tflops},
+                      "algorithmic_frac": (K * steps / t / world) * W_REF_V2[5] / 1e12 / fp64_peak_tflops},
+            **describe(eng, "lane-split (8 lanes per environment)"))
+        eng.exchange.close()
+        del eng
+
+    # ---------------- config[3]: safe-exploration ARS, n = 3, 256 directions ----------------
+    if 256 % world == 0:
+        n3 = 3
+        real = S.make_params(n=n3, l_i=0.8, m_i=1.2, k=10.2)
+        u = np.random.default_rng(7).normal(size=3)
+        u /= np.linalg.norm(u)
+        eps = 1e-3                                  # ars/safe_exploration.py:22-24, 65-80
+        sim = S.make_params(n=n3, m_i=1.2 + eps * u[0], l_i=0.8 + eps * u[1], k=10.2 + eps * u[2])
+        base = dict(N=256, b=256, alpha=0.0075, nu=0.01, H=1000, v2=False, semantics=S.ARS_AGENT, device=device)
+        # pre-trained policy (every rank trains the same one alone: 40 plain iterations from zero) and a fixed
+        # threshold taken from a probe of the simulator returns, so that a realistic share is screened out
+        pre = S.ArsEngine(real, seed=11, distributed=False, use_graph=True, **base)
+        for _ in range(40):
+            pre.run_iteration()
+        W0 = pre.W.clone()
+        probe = S.ArsEngine(real, seed=12, distributed=False, sim_params=sim, sim_threshold=-1e300, initial_policy=W0, **base)
+        probe.run_iteration(update=False)
+        worst = probe.sim_returns.view(256, 2).min(dim=1).values
+        thr = float(torch.quantile(worst, 0.5).cpu())
+        alpha_h = S.Threshold(K=1., A=0.1, B=0.001).compute_alpha(1000)
+        del pre, probe
+
+        def make3(sharded):
+            return S.ArsEngine(real, seed=12, sim_params=sim, sim_threshold=thr, initial_policy=W0, use_graph=True,
+                               distributed=None if sharded else False, **base)
+        par = parity(make3)
+        eng = make3(True)
+        K = 20
+        for _ in range(5):
+            eng.run_iteration()
+        barrier()
+        pass0 = int(eng.n_pass_total.cpu()[0])      # device-side running count of surviving directions (this rank)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):
+            eng.run_iteration()
+        e1.record(stream)
+        barrier()
+        t = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
+        npass = torch.tensor([float(int(eng.n_pass_total.cpu()[0]) - pass0)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(npass)
+        frac_pass = float(npass.cpu()[0]) / (K * 256.0)
+        steps = (2.0 * 256 + 2.0 * 256 * frac_pass) * 1000
+        ee = eng.check_exchange()
+        res["config[3]"] = dict(
+            workload="config[3]: safe-exploration ARS V1 (reward constraint), 3-segment swimmer, 256 directions: 512 simulator "
+                     "rollouts screen every +-delta pair, surviving pairs are rolled out in the real world; real (l,m,k) = "
+                     "(0.8,1.2,10.2), simulator = real + 1e-3 u/|u|, pre-trained W0; sharded over %d GPU(s)" % world,
+            iters_per_s=K / t, ms_per_iter=1e3 * t / K, env_steps_per_s=K * steps / t, iters_timed=K,
+            screened_fraction=1.0 - frac_pass, sim_threshold=thr,
+            threshold_note="threshold = median of min(r+_sim, r-_sim) of a probe iteration; the reference adds "
+                           "alpha(H) * eps = %.3g to its threshold (ars_agent.py:64-69), constant, already inside" % (alpha_h * eps),
+            exchange_epochs=ee, parity_vs_single=par,
+            roofline={"bound": "latency (512 + <=512 envs)",
+                      "executed": {"flops_per_env_step": EXEC_FLOPS["n3_v1"],
+                                   "frac": (K * steps / t / world) * EXEC_FLOPS["n3_v1"] / 1e12 / fp64_peak_tflops}},
+            **describe(eng, "lane-split (4 lanes per environment)"))
+        eng.exchange.close()
+        del eng
+
+    # ---------------- config[4]: n = 10, 4,096 directions x 2 x 128 rollouts ----------------
+    if 4096 % world == 0:
+        def make4(sharded):
+            return S.ArsEngine(S.make_params(n=10), N=4096, b=4096, alpha=0.0075, nu=0.01, H=1000, v2=True,
+                               semantics=S.ARS_AGENT, seed=0, device=device, rollouts_per_direction=128,
+                               init_perturb=1e-2, use_graph=True, distributed=None if sharded else False)
+        par = parity(make4, iters=2)
+        eng = make4(True)
+        K = 3 if world == 1 else 6
+        t = timed(eng, K, 2)
+        steps = 2.0 * 4096 * 128 * 1000
+        ee = eng.check_exchange()
+        res["config[4]"] = dict(
+            workload="config[4]: ARS V2, 10-segment swimmer, 4,096 directions x 2 x 128 rollouts (1,048,576 envs, reset + "
+                     "1e-2*U[0,1) starts), H=1000; directions sharded over %d GPU(s) (strong scaling)" % world,
+            iters_per_s=K / t, ms_per_iter=1e3 * t / K, env_steps_per_s=K * steps / t, iters_timed=K,
+            mean_return_last=float(eng.returns.mean().cpu()), exchange_epochs=ee, parity_vs_single=par,
+            roofline={"bound": "fp64",
+                      "executed": {"flops_per_env_step": EXEC_FLOPS["n10_v2"],
+                                   "frac": (K * steps / t / world) * EXEC_FLOPS["n10_v2"] / 1e12 / fp64_peak_tflops},
+                      "algorithmic_frac": (K * steps / t / world) * W_REF_V2[10] / 1e12 / fp64_peak_tflops},
+            **describe(eng, "one thread per environment, one policy copy per warp"))
+        eng.exchange.close()
+        del eng
+
+    if world == 1:
+        # seed fan-out (ars/experiment.py:64-72: one agent per seed): 32 agents of config[0]
+        # (n=3, V1, 8 directions, H=1000), one CUDA stream + one graph launch per agent-iteration
+        seeds, K3 = 32, 20
+        fan = S.SeedFanout(S.make_params(n=3), range(seeds), N=8, b=8, alpha=0.0075, nu=0.01, H=1000, device=device)
+        fan.run(2)
+        barrier()
+        t0 = time.perf_counter()
+        fan.run(K3, include_initial=False)
+        dt = time.perf_counter() - t0
+        res["config[0] x 32 seeds"] = {
+            "workload": "config[0] x %d seeds: ARS V1, 3-segment swimmer, 8 directions, H=1000, one agent per "
+                        "seed on one GPU (seed fan-out)" % seeds,
+            "agent_iters_per_s": seeds * K3 / dt, "env_steps_per_s": seeds * K3 * 16 * 1000 / dt,
+            "ms_per_round": 1e3 * dt / K3, "timing": "host wall clock around %d rounds incl. final sync" % K3}
+        del fan
+    return res
 
 
 _REAL_STDOUT = None

@@ -244,9 +244,11 @@ SWM_API int swm_ars_update(double* W, int wsize, const double* returns, int N, c
 
 /* mask[k] = (sim_returns[2k] > threshold) && (sim_returns[2k+1] > threshold): the screening rule of
  * ars_agent.py:150-157 (a direction is rolled out in the real world only if both simulated
- * returns exceed the simulator threshold).  n_pass: optional device int32 = number of survivors. */
+ * returns exceed the simulator threshold; a NaN return is screened out as well -- declared deviation from
+ * the reference's `<=`).  n_pass: optional device int32 = number of survivors; n_pass_total: optional
+ * device int64 running total (+= survivors), e.g. the screened fraction of a whole training run. */
 SWM_API int swm_screen_mask(const double* sim_returns, int N, double threshold, int32_t* mask,
-                            int32_t* n_pass, void* stream);
+                            int32_t* n_pass, int64_t* n_pass_total, void* stream);
 
 /* select_action for a batch (ars/environment.py:19-35): actions[B, n-1] = W_e obs_e (V1) or
  * (W_e diag(inv_sigma)) (obs_e - mean) (V2); env e uses policy e / rollouts_per_policy of

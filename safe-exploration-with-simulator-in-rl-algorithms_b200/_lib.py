@@ -114,7 +114,7 @@ def lib():
     L.swm_ars_topb.argtypes = [_dp, _dp, c_int, _dp, _dp]
     L.swm_ars_update.argtypes = [_dp, c_int, _dp, c_int, _dp, c_int, _dp, dbl, c_int, dbl,
                                  ctypes.POINTER(SwmPhilox), _dp, _dp, _dp]
-    L.swm_screen_mask.argtypes = [_dp, c_int, dbl, _dp, _dp, _dp]
+    L.swm_screen_mask.argtypes = [_dp, c_int, dbl, _dp, _dp, _dp, _dp]
     L.swm_policy_actions.argtypes = [pp, _dp, _dp, c_int, _dp, _dp, c_int, _dp, i64, _dp]
     L.swm_philox_deltas.argtypes = [ctypes.POINTER(SwmPhilox), c_int, c_int, _dp, _dp]
     L.swm_fp64_probe.argtypes = [c_int, c_int, c_int, _dp, ctypes.POINTER(dbl), _dp]

@@ -127,7 +127,8 @@ ars_update_kernel(double* __restrict__ W, int wsize, const double* __restrict__ 
 // mask[k] = both simulated returns of direction k exceed the simulator threshold
 // (ars_agent.py:150-157: `reward <= sim_threshold` => no real rollout).
 __global__ void screen_mask_kernel(const double* __restrict__ sim_returns, int N, double threshold,
-                                   int* __restrict__ mask, int* __restrict__ n_pass) {
+                                   int* __restrict__ mask, int* __restrict__ n_pass,
+                                   long long* __restrict__ n_pass_total) {
   __shared__ double red[kArsBlock / 32];
   double c = 0.0;
   for (int k = threadIdx.x; k < N; k += kArsBlock) {
@@ -139,6 +140,7 @@ __global__ void screen_mask_kernel(const double* __restrict__ sim_returns, int N
   }
   c = block_sum(c, red);
   if (threadIdx.x == 0 && n_pass) *n_pass = (int)c;
+  if (threadIdx.x == 0 && n_pass_total) *n_pass_total += (long long)c;
 }
 
 // select_action for a batch (ars/environment.py:19-35)
@@ -321,9 +323,10 @@ extern "C" int swm_ars_update(double* W, int wsize, const double* returns, int N
 }
 
 extern "C" int swm_screen_mask(const double* sim_returns, int N, double threshold, int32_t* mask,
-                               int32_t* n_pass, void* stream) {
+                               int32_t* n_pass, int64_t* n_pass_total, void* stream) {
   if (!sim_returns || !mask || N < 1) return SWM_ERR_BAD_ARG;
-  screen_mask_kernel<<<1, kArsBlock, 0, (cudaStream_t)stream>>>(sim_returns, N, threshold, mask, n_pass);
+  screen_mask_kernel<<<1, kArsBlock, 0, (cudaStream_t)stream>>>(sim_returns, N, threshold, mask, n_pass,
+                                                              reinterpret_cast<long long*>(n_pass_total));
   return SWM_CHECK_LAUNCH();
 }
 

@@ -87,6 +87,7 @@ class ArsEngine:
         if sim_params is not None:
             self.mask_local = torch.ones(self.N_local, dtype=torch.int32, device=self.device)
             self.n_pass_local = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.n_pass_total = torch.zeros(1, dtype=torch.int64, device=self.device)  # survivors so far (this rank)
             self.mask = torch.ones(self.N, dtype=torch.int32, device=self.device)
             self.sim_returns = torch.zeros(2 * self.N_local, **f64)
         self.last = None
@@ -155,7 +156,7 @@ class ArsEngine:
             sim = self._rollouts(self.sim_params, self._sim_out, deltas_local, None, False, False, None)
             sim_ret = sim.returns if R == 1 else ops.reduce_returns(sim.returns, R, out=self.sim_returns)
             self.sim_returns = sim_ret
-            ops.screen_mask(sim_ret, self.sim_threshold, self.mask_local, self.n_pass_local)
+            ops.screen_mask(sim_ret, self.sim_threshold, self.mask_local, self.n_pass_local, self.n_pass_total)
             dir_mask = self.mask_local
         res = self._rollouts(self.params, self._out, deltas_local, dir_mask, self.v2, want_trajectory,
                              self.step_screen)

@@ -430,15 +430,17 @@ def ars_update(W, returns, N, *, order=None, n_order=None, divisor=0.0, ddof=0, 
     return W
 
 
-def screen_mask(sim_returns, threshold, mask_out=None, n_pass_out=None):
-    """mask[k] = r_sim+_k > threshold and r_sim-_k > threshold (ars_agent.py:150-157)."""
+def screen_mask(sim_returns, threshold, mask_out=None, n_pass_out=None, n_pass_total=None):
+    """mask[k] = r_sim+_k > threshold and r_sim-_k > threshold (ars_agent.py:150-157).  n_pass_total: optional
+    int64 device tensor accumulating the number of survivors over calls."""
     N = sim_returns.numel() // 2
     dev = sim_returns.device
     mask = torch.empty(N, dtype=torch.int32, device=dev) if mask_out is None else mask_out
     n_pass = torch.empty(1, dtype=torch.int32, device=dev) if n_pass_out is None else n_pass_out
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().swm_screen_mask(_lib.ptr(sim_returns), N, float(threshold),
-                                              _lib.ptr(mask), _lib.ptr(n_pass), _lib.stream_ptr()))
+                                              _lib.ptr(mask), _lib.ptr(n_pass), _lib.ptr(n_pass_total),
+                                              _lib.stream_ptr()))
     return mask, n_pass
 
 
