@@ -317,6 +317,31 @@ SWM_API int swm_exchange_status(swm_exchange_t* h, uint64_t* epoch, uint64_t* st
 SWM_API int swm_exchange_destroy(swm_exchange_t* h);
 SWM_API int swm_ars_pack_exchange(swm_exchange_t* h, const swm_pack_t* p, void* stream);
 
+/* ---- The RL-Glue ARS experiment with the reference's literal step-level state machine -------------------
+ * Replaces the four-process loop of rlglue/experiment/SwimmerExperiment.cpp:65-100 (2 N H training RL_steps
+ * with "load state" every H steps, "freeze training", one H-step evaluation rollout per iteration) driving
+ * rlglue/agent/SwimmerAgent.py:79-241 against rlglue/environment/SwimmerEnvironment.cpp.  The reference's
+ * bookkeeping couples consecutive rollouts (see csrc/rlglue_protocol.cu), so an experiment is sequential: one
+ * thread per replica.  state[replicas, swm_rlglue_protocol_state_doubles(n)] = [policy | pending action |
+ * running total | iterations done]; all zeros = a fresh experiment (agent_start); calls continue where the
+ * previous one stopped.  deltas: [iterations done + n_it, N, (n-1)(2n+2)] U[0,1) draws shared by all replicas
+ * (replaying the agent's np.random.rand), or NULL: Philox, key seed + replica, counter (pair, direction,
+ * iteration0 + iteration, 0). */
+typedef struct {
+  int32_t N, b, H, n_it;
+  double alpha, nu;
+  const double* deltas;
+  uint64_t seed;
+  uint32_t iteration0;
+  int32_t _pad;
+  double* state;    /* in/out */
+  double* results;  /* out [replicas, n_it]: evaluation totals = the lines of rlglue/plot/results.txt */
+  double* table;    /* out [replicas, n_it, 2N]: the agent's reward table at each update */
+  int64_t replicas;
+} swm_rlglue_protocol_t;
+SWM_API int64_t swm_rlglue_protocol_state_doubles(int n);
+SWM_API int swm_rlglue_protocol(const swm_params_t* params, const swm_rlglue_protocol_t* cfg, void* stream);
+
 /* FP64 pipe probe: every thread runs `iters` x 8 independent DFMA chains; returns through
  * *flops_out (host) the number of floating-point operations executed (2 per DFMA).  Used by
  * bench.py to measure the FP64 roofline denominator on the box (MEASURED_PEAKS.json has none). */

@@ -286,6 +286,24 @@ def rlglue(ref):
     np.savez(os.path.join(OUT, "rlglue_step.npz"), **out)
 
 
+def rlglue_agent(ref):
+    """The UNMODIFIED rlglue/agent/SwimmerAgent.py driven against the UNMODIFIED compiled C++ swimmer the way
+    rlglue/experiment/SwimmerExperiment.cpp:65-100 drives them (oracle/rlglue_protocol.py emulates the RL-Glue
+    runtime in process).  Case a: today's rlglue/parameters.txt (N = b = 1, H = 1000); case b: several
+    directions, b < N, five segments."""
+    from oracle import rlglue_protocol as RP
+    out = {}
+    base = dict(n_seg=3, direction=(1.0, 0.0), h_global=0.01, N=1, b=1, H=1000, alpha=0.02, nu=0.02, max_u=5.,
+                l_i=1., k=10., m_i=1.)
+    for tag, par, n_it, seed in (("a", base, 6, 5), ("b", dict(base, n_seg=5, N=3, b=2, H=150, alpha=0.05, nu=0.3), 4, 9)):
+        r = RP.run_reference_protocol(par, n_it, seed)
+        out[tag + "_par"] = np.array([par["n_seg"], par["N"], par["b"], par["H"], par["alpha"], par["nu"], par["max_u"],
+                                      par["l_i"], par["k"], par["m_i"], par["h_global"]])
+        for k, v in r.items():
+            out[tag + "_" + k] = v
+    np.savez(os.path.join(OUT, "rlglue_agent.npz"), **out)
+
+
 def misc(ref):
     out = {}
     vals = []
@@ -303,6 +321,7 @@ def main():
     topb(ref)
     misc(ref)
     rlglue(ref)
+    rlglue_agent(ref)
     safe_ars_runs(ref)
     ars_agent_safe(ref)
     ars_agent_runs(ref)

@@ -63,6 +63,14 @@ class SwmPack(ctypes.Structure):
                 ("record_out", _dp), ("gathered_in", _dp)]
 
 
+class SwmRlglueProtocol(ctypes.Structure):
+    """swm_rlglue_protocol_t (include/swimmer_ars.h)."""
+    _fields_ = [("N", ctypes.c_int32), ("b", ctypes.c_int32), ("H", ctypes.c_int32), ("n_it", ctypes.c_int32),
+                ("alpha", ctypes.c_double), ("nu", ctypes.c_double), ("deltas", _dp), ("seed", ctypes.c_uint64),
+                ("iteration0", ctypes.c_uint32), ("_pad", ctypes.c_int32), ("state", _dp), ("results", _dp),
+                ("table", _dp), ("replicas", ctypes.c_int64)]
+
+
 IPC_HANDLE_BYTES = 64  # SWM_IPC_HANDLE_BYTES
 
 
@@ -121,6 +129,9 @@ def lib():
     L.swm_counter_add.argtypes = [_dp, ctypes.c_uint32, _dp]
     L.swm_record_nanmean.argtypes = [_dp, c_int, _dp, _dp, ctypes.c_uint32, _dp]
     L.swm_rlglue_set_params.argtypes = [pp]
+    L.swm_rlglue_protocol_state_doubles.argtypes = [c_int]
+    L.swm_rlglue_protocol_state_doubles.restype = i64
+    L.swm_rlglue_protocol.argtypes = [pp, ctypes.POINTER(SwmRlglueProtocol), _dp]
     L.swm_pack_record_doubles.argtypes = [c_int, c_int, c_int]
     L.swm_pack_record_doubles.restype = i64
     L.swm_exchange_create.argtypes = [c_int, c_int, i64, ctypes.POINTER(_dp)]

@@ -9,6 +9,10 @@
 
 using namespace swm;
 
+namespace swm {
+Phys make_phys_public(const swm_params_t* p);
+}
+
 namespace {
 
 thread_local char g_cuda_err[256] = "";
@@ -59,6 +63,13 @@ Phys make_phys(const swm_params_t* p) {
   P.I = m * (l * l) / 12.0;
   return P;
 }
+
+}  // namespace
+
+// shared with rlglue_protocol.cu
+Phys swm::make_phys_public(const swm_params_t* p) { return make_phys(p); }
+
+namespace {
 
 #define SWM_DISPATCH_N(n, CALL)                 \
   switch (n) {                                  \

@@ -195,3 +195,33 @@ def test_safe_step_rollouts_match_reference(O):
 def test_threshold_alpha(O):
     for K, A, B, H, want in golden("misc.npz")["threshold_alpha"]:
         assert abs(O.threshold_alpha(K, A, B, int(H)) - want) <= 1e-12 * abs(want)
+
+
+def _rlglue_par(g, tag):
+    n, N, b, H, alpha, nu, max_u, l_i, k, m_i, h = g[tag + "_par"]
+    return dict(n_seg=int(n), N=int(N), b=int(b), H=int(H), alpha=alpha, nu=nu, max_u=max_u, l_i=l_i, k=k, m_i=m_i,
+                h_global=h, direction=(1.0, 0.0))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_rlglue_agent_protocol_restatement_matches_unmodified_agent(O, tag):
+    """tests/golden/rlglue_agent.npz = the UNMODIFIED rlglue/agent/SwimmerAgent.py driven against the UNMODIFIED
+    compiled C++ swimmer the way SwimmerExperiment.cpp:65-100 does (oracle/rlglue_protocol.py).  The restated
+    step-level loop over the C port reproduces its evaluation returns and policies, which pins the agent state
+    machine (:79-130), the clip (:181-201), the U[0,1) perturbations as drawn (:203-212) and the index-order /
+    sample-stdev update (:214-241)."""
+    from oracle import rlglue_protocol as RP
+    g = golden("rlglue_agent.npz")
+    par = _rlglue_par(g, tag)
+    n_it = len(g[tag + "_results"])
+    res, pol = RP.restated_protocol(par, n_it, g[tag + "_deltas"])
+    np.testing.assert_allclose(res, g[tag + "_results"], rtol=1e-11)
+    np.testing.assert_allclose(pol, g[tag + "_policies"], rtol=1e-9, atol=1e-13)
+    # the oracle's update rule "semantics 2" (first b directions, sample stdev, divisor b) against the policy
+    # steps the unmodified agent took from its own reward tables
+    for it in range(n_it):
+        W, _ = O.update_policy(g[tag + "_policies"][it], g[tag + "_deltas"][it], g[tag + "_rewards"][it],
+                               b=par["b"], alpha=par["alpha"], semantics=2)
+        np.testing.assert_allclose(W, g[tag + "_policies"][it + 1], rtol=1e-9, atol=1e-13)
+    # the reference's literal quirk: in iteration 0 the last slot of the reward table holds one step's reward
+    assert abs(g[tag + "_rewards"][0][-1]) < 2e-3 < abs(g[tag + "_rewards"][0][0])

@@ -468,3 +468,38 @@ def test_v2_safe_engine_with_everything_screened_out_keeps_identity_normalisatio
     # a NaN simulator return is screened out (declared deviation from the reference's `<=`)
     m, cnt = S.ops.screen_mask(torch.tensor([1.0, float("nan"), 1.0, 2.0], dtype=torch.float64, device="cuda"), 0.0)
     assert m.tolist() == [0, 1] and int(cnt) == 1
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_rlglue_reference_protocol_kernel_matches_unmodified_agent(S, O, tag):
+    """RlglueArsExperiment(protocol='reference') = the reference's literal step-level loop (csrc/rlglue_protocol.cu)
+    against the fixture produced by the unmodified agent + compiled C++ swimmer (tests/golden/rlglue_agent.npz),
+    replaying the agent's own U[0,1) draws: evaluation returns, reward tables and policies to 1e-9."""
+    g = golden("rlglue_agent.npz")
+    n, N, b, H, alpha, nu, max_u, l_i, k, m_i, h = g[tag + "_par"]
+    kw = dict(n_seg=int(n), N=int(N), b=int(b), H=int(H), alpha=alpha, nu=nu, max_u=max_u, l_i=l_i, k=k, m_i=m_i,
+              h_global=h)
+    n_it = len(g[tag + "_results"])
+    ex = S.RlglueArsExperiment(protocol="reference", **kw)
+    # in two calls: the experiment continues where it stopped
+    r1, t1 = ex.run_reference_protocol(2, deltas=g[tag + "_deltas"])
+    r2, t2 = ex.run_reference_protocol(n_it - 2, deltas=g[tag + "_deltas"])
+    res = torch.cat([r1, r2], dim=1)[0].cpu().numpy()
+    tab = torch.cat([t1, t2], dim=1)[0].cpu().numpy()
+    np.testing.assert_allclose(res, g[tag + "_results"], rtol=1e-9)
+    np.testing.assert_allclose(tab, g[tag + "_rewards"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(ex.policy, g[tag + "_policies"][-1], rtol=1e-8, atol=1e-12)
+    # Philox perturbations, several replicas: against the restated loop fed with the same Philox draws
+    from oracle import rlglue_protocol as RP
+    par = dict(kw, direction=(1.0, 0.0))
+    ws = (int(n) - 1) * (2 * int(n) + 2)
+    ex2 = S.RlglueArsExperiment(protocol="reference", seed=77, replicas=3, **kw)
+    got = ex2.run_reference_protocol(2)[0].cpu().numpy()
+    for rep in (0, 2):
+        d = np.stack([[O.philox_delta(77 + rep, it, kdir, ws, dist=1).reshape(int(n) - 1, -1) for kdir in range(int(N))]
+                      for it in range(3)])
+        want, _ = RP.restated_protocol(par, 2, d)
+        np.testing.assert_allclose(got[rep], want, rtol=1e-9)
+    # the drop-in class front end
+    ex3 = S.RlglueArsExperiment(protocol="reference", seed=77, **kw)
+    np.testing.assert_allclose(ex3.run_training(2), got[0], rtol=0, atol=0)
