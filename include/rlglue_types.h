@@ -34,16 +34,10 @@ typedef struct {
   int terminal;
 } reward_observation_terminal_t;
 
-/* RLStruct_util.h equivalents: the callee owns the arrays (SwimmerEnvironment.cpp:20-21,72-73). */
-#if defined(__GNUC__)
-__attribute__((visibility("default")))
-#endif
-void allocateRLStruct(rl_abstract_type_t* dst, unsigned int numInts, unsigned int numDoubles,
-                      unsigned int numChars);
-#if defined(__GNUC__)
-__attribute__((visibility("default")))
-#endif
-void clearRLStruct(rl_abstract_type_t* dst);
+/* rlglue/utils/C/RLStruct_util.h (allocateRLStruct / clearRLStruct) is deliberately NOT declared or
+ * exported here: a real RL-Glue build links -lrlutils, which defines those symbols, and a second default-
+ * visibility definition in libswimmer_ars.so would interpose on it.  The shim allocates its two observation
+ * structs with private helpers (csrc/rlglue_env_shim.cu). */
 
 #ifdef __cplusplus
 }

@@ -25,10 +25,26 @@ observation_t this_observation;
 observation_t saved_observation;
 reward_observation_terminal_t this_reward_observation;
 swm_params_t g_params = {3, 0, 1.0, 1.0, 10.0, 0.01, 5.0, {1.0, 0.0}};
-double* d_state = nullptr;   // [2n+2]
-double* d_action = nullptr;  // [n-1]
-double* d_reward = nullptr;  // [1]
+// One step = one upload, one launch, one download on a private stream, through pinned staging buffers:
+double* d_in = nullptr;      // device [2n+2 state | n-1 action]
+double* d_out = nullptr;     // device [2n+2 next state | reward]
+double* h_in = nullptr;      // pinned mirror of d_in
+double* h_out = nullptr;     // pinned mirror of d_out
+cudaStream_t g_stream = nullptr;
 std::string g_task_spec, g_param_msg;
+
+// private stand-ins for RLStruct_util.h (not exported: librlutils owns those names)
+void shim_alloc(rl_abstract_type_t* dst, unsigned int numDoubles) {
+  dst->numInts = 0; dst->numDoubles = numDoubles; dst->numChars = 0;
+  dst->intArray = nullptr;
+  dst->doubleArray = numDoubles ? (double*)calloc(numDoubles, sizeof(double)) : nullptr;
+  dst->charArray = nullptr;
+}
+void shim_clear(rl_abstract_type_t* dst) {
+  free(dst->doubleArray);
+  dst->intArray = nullptr; dst->doubleArray = nullptr; dst->charArray = nullptr;
+  dst->numInts = dst->numDoubles = dst->numChars = 0;
+}
 
 void die(const char* what) {
   fprintf(stderr, "swimmer rlglue shim: %s (%s)\n", what, swm_last_cuda_error());
@@ -64,20 +80,6 @@ void copy_obs(observation_t& dst, const observation_t& src) {
 
 extern "C" {
 
-void allocateRLStruct(rl_abstract_type_t* dst, unsigned int numInts, unsigned int numDoubles,
-                      unsigned int numChars) {
-  dst->numInts = numInts; dst->numDoubles = numDoubles; dst->numChars = numChars;
-  dst->intArray = numInts ? (int*)calloc(numInts, sizeof(int)) : nullptr;
-  dst->doubleArray = numDoubles ? (double*)calloc(numDoubles, sizeof(double)) : nullptr;
-  dst->charArray = numChars ? (char*)calloc(numChars + 1, 1) : nullptr;
-}
-
-void clearRLStruct(rl_abstract_type_t* dst) {
-  free(dst->intArray); free(dst->doubleArray); free(dst->charArray);
-  dst->intArray = nullptr; dst->doubleArray = nullptr; dst->charArray = nullptr;
-  dst->numInts = dst->numDoubles = dst->numChars = 0;
-}
-
 /* Programmatic alternative to the "set parameters" message (the reference has file globals). */
 int swm_rlglue_set_params(const swm_params_t* p) {
   if (!p || p->n < SWM_MIN_SEGMENTS || p->n > SWM_MAX_SEGMENTS) return SWM_ERR_BAD_ARG;
@@ -87,15 +89,17 @@ int swm_rlglue_set_params(const swm_params_t* p) {
 
 const char* env_init(void) {
   const int n_obs = 2 + 2 * g_params.n, n_action = g_params.n - 1;
-  allocateRLStruct(&this_observation, 0, n_obs, 0);
-  allocateRLStruct(&saved_observation, 0, n_obs, 0);
+  shim_alloc(&this_observation, n_obs);
+  shim_alloc(&saved_observation, n_obs);
   this_reward_observation.observation = &this_observation;
   this_reward_observation.reward = 0;
   this_reward_observation.terminal = 0;
-  if (cudaMalloc(&d_state, sizeof(double) * n_obs) != cudaSuccess ||
-      cudaMalloc(&d_action, sizeof(double) * (n_action > 0 ? n_action : 1)) != cudaSuccess ||
-      cudaMalloc(&d_reward, sizeof(double)) != cudaSuccess)
-    die("cudaMalloc failed");
+  if (cudaMalloc(&d_in, sizeof(double) * (n_obs + n_action)) != cudaSuccess ||
+      cudaMalloc(&d_out, sizeof(double) * (n_obs + 1)) != cudaSuccess ||
+      cudaMallocHost(&h_in, sizeof(double) * (n_obs + n_action)) != cudaSuccess ||
+      cudaMallocHost(&h_out, sizeof(double) * (n_obs + 1)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess)
+    die("device / pinned allocation failed");
   g_task_spec = "VERSION RL-Glue-3.0 PROBLEMTYPE continuing DISCOUNTFACTOR 0.9 OBSERVATIONS DOUBLES (" +
                 std::to_string(n_obs) + " UNSPEC UNSPEC) ACTIONS DOUBLES (" + std::to_string(n_action) +
                 " " + std::to_string(-g_params.max_u) + " " + std::to_string(g_params.max_u) +
@@ -119,26 +123,29 @@ const reward_observation_terminal_t* env_step(const action_t* this_action) {
     this_reward_observation.terminal = 1;
     return &this_reward_observation;
   }
-  if (cudaMemcpy(d_state, this_observation.doubleArray, sizeof(double) * n_obs, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(d_action, this_action->doubleArray, sizeof(double) * n_action, cudaMemcpyHostToDevice) != cudaSuccess)
+  memcpy(h_in, this_observation.doubleArray, sizeof(double) * n_obs);
+  memcpy(h_in + n_obs, this_action->doubleArray, sizeof(double) * n_action);
+  if (cudaMemcpyAsync(d_in, h_in, sizeof(double) * (n_obs + n_action), cudaMemcpyHostToDevice, g_stream) != cudaSuccess)
     die("H2D copy failed");
-  if (swm_step_batched(&g_params, SWM_DYN_RLGLUE, d_state, d_action, d_state, d_reward, 1, nullptr) != SWM_OK)
+  if (swm_step_batched(&g_params, SWM_DYN_RLGLUE, d_in, d_in + n_obs, d_out, d_out + n_obs, 1, g_stream) != SWM_OK)
     die("swm_step_batched failed");
-  double reward = 0.0;
-  if (cudaMemcpy(this_observation.doubleArray, d_state, sizeof(double) * n_obs, cudaMemcpyDeviceToHost) != cudaSuccess ||
-      cudaMemcpy(&reward, d_reward, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+  if (cudaMemcpyAsync(h_out, d_out, sizeof(double) * (n_obs + 1), cudaMemcpyDeviceToHost, g_stream) != cudaSuccess ||
+      cudaStreamSynchronize(g_stream) != cudaSuccess)
     die("D2H copy failed");
+  memcpy(this_observation.doubleArray, h_out, sizeof(double) * n_obs);
   this_reward_observation.observation = &this_observation;
-  this_reward_observation.reward = reward;
+  this_reward_observation.reward = h_out[n_obs];
   this_reward_observation.terminal = 0;
   return &this_reward_observation;
 }
 
 void env_cleanup(void) {
-  clearRLStruct(&this_observation);
-  clearRLStruct(&saved_observation);
-  cudaFree(d_state); cudaFree(d_action); cudaFree(d_reward);
-  d_state = d_action = d_reward = nullptr;
+  shim_clear(&this_observation);
+  shim_clear(&saved_observation);
+  cudaFree(d_in); cudaFree(d_out); cudaFreeHost(h_in); cudaFreeHost(h_out);
+  if (g_stream) cudaStreamDestroy(g_stream);
+  d_in = d_out = h_in = h_out = nullptr;
+  g_stream = nullptr;
 }
 
 const char* env_message(const char* message) {

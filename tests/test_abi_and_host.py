@@ -17,8 +17,6 @@ def _declared_symbols():
     for h in ("swimmer_ars.h", "swimmer_rlglue_env.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         names += re.findall(r"^SWM_API[^;(]*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", src, flags=re.M)
-    src = open(os.path.join(ROOT, "include", "rlglue_types.h")).read()
-    names += re.findall(r"\bvoid\s+(allocateRLStruct|clearRLStruct)\s*\(", src)
     return sorted(set(names))
 
 
@@ -28,6 +26,9 @@ def test_library_exports_every_declared_symbol(S):
     assert len(names) >= 25 and "swm_rollout" in names and "env_step" in names
     for name in names:
         assert hasattr(L, name), "missing export: " + name
+    # RL-Glue's own utility symbols must NOT be exported: -lrlutils defines them in a real RL-Glue build
+    for name in ("allocateRLStruct", "clearRLStruct"):
+        assert not hasattr(L, name), "would interpose on librlutils: " + name
 
 
 def test_struct_layouts_match_build(S):
