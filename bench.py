@@ -320,22 +320,34 @@ def run_b200(args):
         return float(t.cpu()[0])
 
     def single_launch():
-        return S.ops.rollout(params, H, actions=actions, want_final=True, out=out)
+        return S.ops.rollout(params, H, actions=actions, want_final=True, out=out, schedule="plain")
 
-    # The timed step: the same batch scheduled as 16 sub-batches x 64-step chunks on 16 streams
-    # (ops.ChunkedRollout: swm_rollout launches chained through final_state -> init_state, replayed from one
-    # CUDA graph).  Every final state is bit-identical to the single launch; short launches from several
-    # streams remove the quantisation of 65,536 envs over the SM sub-partitions (3.46 warps each).
-    plan = S.SwimmerEnv(n=N_SEG, device=device).rollout_plan(H, n_sub=16, chunk=64, actions=actions)
-    plan.run()
+    # The timed step: ONE call of the public batched entry point with no tuning argument --
+    # SwimmerEnv.rollout_batched(H, actions) -> swm_rollout -- captured once in a CUDA graph and replayed.  For this
+    # batch (3.46 warps per SM sub-partition) the library itself schedules the rollout as sub-batches x 64-step
+    # chunks on internal streams (swm_rollout_t.schedule_sub = 0: decided from B, n and the SM count; 16 x 64 while
+    # capturing, 8 x 256 when enqueued eagerly); every final state is bit-identical to one plain launch.
+    env0 = S.SwimmerEnv(n=N_SEG, device=device)
+    out_def = {"returns": torch.empty_like(out["returns"]), "final_state": torch.empty_like(out["final_state"])}
+
+    def default_call():
+        return env0.rollout_batched(H, actions=actions, want_final=True, out=out_def)
+    default_call()
     torch.cuda.synchronize()
     step_graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(step_graph):
-        plan.run()
+        default_call()
+        import ctypes as _ct
+        _cfg = S._lib.SwmRollout()
+        _cfg.policy_mode, _cfg.H, _cfg.B, _cfg.rollouts_per_policy = 0, H, B_PER_GPU, 1
+        _cfg.actions, _cfg.returns, _cfg.final_state = actions.data_ptr(), out_def["returns"].data_ptr(), out_def["final_state"].data_ptr()
+        _ns, _ch = _ct.c_int(0), _ct.c_int(0)
+        S._lib.lib().swm_rollout_schedule(_ct.byref(params), _ct.byref(_cfg), S._lib.stream_ptr(), _ct.byref(_ns), _ct.byref(_ch))
+    launches_per_step = max(1, _ns.value) * (-(-H // _ch.value) if _ns.value else 1)
     ref_res = single_launch()
     step_graph.replay()
     torch.cuda.synchronize()
-    assert torch.equal(plan.state, ref_res.final_state), "chunked schedule must reproduce the single launch"
+    assert torch.equal(out_def["final_state"], ref_res.final_state), "library schedule must reproduce the single launch"
 
     def one_step():
         step_graph.replay()
@@ -371,17 +383,21 @@ def run_b200(args):
     barrier()
     wall = time.perf_counter() - t_wall0
     t_dev_s = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)) * 1e-3
-    # ---- supplementary: one plain swm_rollout launch per step (no chunking), same timing method ----
-    evs1 = []
-    for _ in range(args.steps):
-        flush.fill_(1.0)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        single_launch()
-        e1.record(stream)
-        evs1.append((e0, e1))
-    barrier()
-    t_single_s = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs1)) * 1e-3
+    # ---- supplementary: one plain swm_rollout launch per step (no chunking), and the default call enqueued
+    # eagerly (no graph), same timing method ----
+    def timed_steps(fn):
+        ev = []
+        for _ in range(args.steps):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            ev.append((e0, e1))
+        barrier()
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) * 1e-3
+    t_single_s = timed_steps(single_launch)
+    t_eager_s = timed_steps(default_call)
 
     # ---- supplementary: the same K launches with TWO in flight (two streams, device-resident inputs, no
     # flush).  One config[1] batch is only 3.46 warps per SM sub-partition; two batches fill the FP64 pipe. ----
@@ -395,7 +411,7 @@ def run_b200(args):
         st.wait_stream(stream)
     for k in range(args.steps):
         with torch.cuda.stream(side[k & 1]):
-            S.ops.rollout(params, H, actions=actions, want_final=True, out=outs2[k & 1])  # plain launches
+            S.ops.rollout(params, H, actions=actions, want_final=True, out=outs2[k & 1], schedule="plain")
     for st in side:
         stream.wait_stream(st)
     c1.record(stream)
@@ -432,6 +448,7 @@ def run_b200(args):
     e2e_value = total_steps / t_e2e_s
     conc_value = total_steps / t_conc_s
     single_value = total_steps / t_single_s
+    eager_value = total_steps / t_eager_s
 
     # ---- sustained run: the timed step replayed back to back for >= 2 s (no flush, no host gaps) with the
     # clock / power samples of exactly that window: the 18 ms headline survives thermals and the power cap ----
@@ -481,9 +498,10 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(CONFIG),
             "run": {"l2": "flushed between steps (256 MiB write outside the timed events); inputs 1 MiB",
-                    "schedule": "each step = one CUDA-graph launch of %d swm_rollout kernels: 16 sub-batches x "
-                                "64-step chunks on 16 streams, state chained through final_state -> init_state, "
-                                "final states bit-identical to a single launch" % plan.launches,
+                    "schedule": "each step = SwimmerEnv.rollout_batched(H, actions) with NO schedule argument, captured in a "
+                                "CUDA graph: the library picked %d sub-batches x %d-step chunks (%d kernel launches per "
+                                "step, state chained through final_state, final states bit-identical to one plain "
+                                "launch)" % (_ns.value, _ch.value, launches_per_step),
                     "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
             "roofline": {"bound": "fp64", "achieved": exec_tf, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                          "frac": exec_tf / fp64_peak_tflops, "flops_per_env_step": EXEC_FLOPS["n3_fixed"],
@@ -505,8 +523,11 @@ def run_b200(args):
                     "api": "SwimmerEnv.rollout_batched_host: pinned host actions in, pinned host returns + final states "
                            "out every step, double-buffered on two streams; CUDA events around all K steps"},
             "single_launch": {"value": single_value, "unit": UNIT,
-                              "note": "one plain swm_rollout launch per step (the whole batch in one kernel, no "
-                                      "chunking), same events / flush as `value`"},
+                              "note": "one plain swm_rollout launch per step (schedule forced to 'plain': the whole batch in "
+                                      "one kernel), same events / flush as `value`"},
+            "default_api_eager": {"value": eager_value, "unit": UNIT,
+                                  "note": "the same default call enqueued eagerly every step (no CUDA graph): the library "
+                                          "then uses 8 sub-batches x 256-step chunks (32 launches)"},
             "two_in_flight": {"value": conc_value, "unit": UNIT, "streams": 2,
                               "roofline_frac_executed": (conc_value / world) * EXEC_FLOPS["n3_fixed"] / 1e12 / fp64_peak_tflops,
                               "note": "same kernel, same inputs resident in HBM, K launches alternating on two streams "
@@ -514,7 +535,7 @@ def run_b200(args):
                                       "holds 4), two batches in flight balance and fill the FP64 pipe; this is also why "
                                       "the double-buffered e2e number exceeds the one-launch-at-a-time `value`"},
             "sustained": sustained,
-            "gpu_launches": args.steps * plan.launches, "clocks": clocks, "cpu_baseline": cpu,
+            "gpu_launches": args.steps * launches_per_step, "clocks": clocks, "cpu_baseline": cpu,
             "wall_s_timed_region": wall,
         }
         line.update(extra_cpu)

@@ -159,6 +159,13 @@ typedef struct {
                                    mid-size batches over SM sub-partitions; chunk lengths that are multiples of 64
                                    keep the visited states bit-identical to the single launch. */
   int32_t kernel;               /* swm_rollout_kernel: 0 = chosen from (B, n, SM count) */
+  int32_t schedule_sub;         /* 0: the library decides between one plain launch and a chunked schedule (sub-batches x
+                                   64-step-aligned time chunks on internal streams, joined back into `stream`; needs
+                                   final_state as the chaining buffer; results: states bit-identical, returns equal up to
+                                   the rounding of the partial sums) from (B, n, SM count) -- see swm_rollout_schedule;
+                                   -1: always one plain launch;  1..16: this many sub-batches (SWM_ERR_UNSUPPORTED if the
+                                   request cannot be scheduled: trajectory / screening / no final_state / H <= chunk) */
+  int32_t schedule_chunk;       /* steps per chunk when schedule_sub > 0: a positive multiple of 64 */
 } swm_rollout_t;
 
 SWM_API int swm_abi_version(void);
@@ -190,12 +197,17 @@ SWM_API int swm_accelerations_batched(const swm_params_t* params, int variant, c
                               const double* action, double* acc, int64_t B, void* stream);
 
 SWM_API int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg, void* stream);
-/* number of per-block rows the rollout kernel writes into stats_partial for B envs (depends on the kernel
- * swm_rollout will choose for this cfg on the current device) */
-SWM_API int64_t swm_rollout_stats_blocks(const swm_params_t* params, const swm_rollout_t* cfg);
+/* number of per-block rows swm_rollout writes into stats_partial for this cfg when launched on `stream` of the
+ * current device (depends on the kernel and the schedule it will choose; the schedule may differ while `stream`
+ * is capturing a CUDA graph) */
+SWM_API int64_t swm_rollout_stats_blocks(const swm_params_t* params, const swm_rollout_t* cfg, void* stream);
 /* which kernel swm_rollout would run for this cfg on the current device: SWM_KERNEL_THREAD / _LANES,
  * or a negative swm_status */
 SWM_API int swm_rollout_kernel_choice(const swm_params_t* params, const swm_rollout_t* cfg);
+/* the schedule swm_rollout would use on `stream`: *n_sub = 0 for one plain launch, else sub-batches x *chunk
+ * steps (finer while the stream is capturing a CUDA graph: replayed launches have no host cost) */
+SWM_API int swm_rollout_schedule(const swm_params_t* params, const swm_rollout_t* cfg, void* stream, int* n_sub,
+                                 int* chunk);
 
 /* Deterministic Welford bookkeeping for ARS V2 (replaces np.mean / np.cov over the growing
  * saved_states list, ars/ars_agent.py:179-182).  A statistics record is

@@ -51,7 +51,8 @@ class SwmRollout(ctypes.Structure):
                 ("inv_sigma", _dp), ("init_state", _dp), ("init_state_count", ctypes.c_int64),
                 ("init_perturb", ctypes.c_double), ("returns", _dp), ("final_state", _dp),
                 ("trajectory", _dp), ("stats_partial", _dp), ("stats_pivot", _dp),
-                ("screen", SwmScreen), ("accumulate_returns", ctypes.c_int32), ("kernel", ctypes.c_int32)]
+                ("screen", SwmScreen), ("accumulate_returns", ctypes.c_int32), ("kernel", ctypes.c_int32),
+                ("schedule_sub", ctypes.c_int32), ("schedule_chunk", ctypes.c_int32)]
 
 
 class SwmPack(ctypes.Structure):
@@ -113,9 +114,10 @@ def lib():
     L.swm_accelerations_batched.argtypes = [pp, c_int, _dp, _dp, _dp, i64, _dp]
     L.swm_step_batched_models.argtypes = [pp, c_int, i64, _dp, _dp, _dp, _dp, _dp]
     L.swm_rollout.argtypes = [pp, ctypes.POINTER(SwmRollout), _dp]
-    L.swm_rollout_stats_blocks.argtypes = [pp, ctypes.POINTER(SwmRollout)]
+    L.swm_rollout_stats_blocks.argtypes = [pp, ctypes.POINTER(SwmRollout), _dp]
     L.swm_rollout_stats_blocks.restype = i64
     L.swm_rollout_kernel_choice.argtypes = [pp, ctypes.POINTER(SwmRollout)]
+    L.swm_rollout_schedule.argtypes = [pp, ctypes.POINTER(SwmRollout), _dp, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
     L.swm_stats_finalize.argtypes = [_dp, i64, c_int, dbl, _dp, _dp, _dp, _dp]
     L.swm_stats_merge.argtypes = [_dp, _dp, c_int, c_int, _dp, _dp, _dp]
     L.swm_reduce_returns.argtypes = [_dp, i64, c_int, _dp, _dp]

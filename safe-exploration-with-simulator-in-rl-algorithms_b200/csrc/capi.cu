@@ -4,6 +4,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "errors.cuh"
 #include "lane_launch.cuh"
 
@@ -266,16 +268,194 @@ extern "C" int swm_rollout_kernel_choice(const swm_params_t* params, const swm_r
   return choose_kernel(params->n, cfg, a, f);
 }
 
-extern "C" int64_t swm_rollout_stats_blocks(const swm_params_t* params, const swm_rollout_t* cfg) {
+namespace {
+
+// ---- chunked schedule of one rollout: sub-batches x 64-step-aligned time chunks on internal streams -------
+// One thread owns one environment for all H steps, so a batch that leaves a fractional number of warps per SM
+// sub-partition between 3 and 4 (65,536 three-segment envs on 148 SMs: 3.46, the busiest holds 4) runs at the
+// pace of the busiest sub-partition.  Cutting the rollout into short launches on several streams (state chained
+// through final_state -> init_state, returns accumulated, chunk boundaries on the exact re-evaluation of the
+// tracked sines/cosines so that every state is bit-identical) lets the hardware re-balance every 64 steps.
+constexpr int kPlanMaxSub = 16;
+
+struct Plan {
+  int n_sub = 0, chunk = 0;  // n_sub == 0: one plain launch
+};
+
+struct PlanStreams {
+  cudaStream_t s[kPlanMaxSub];
+  cudaEvent_t fork, join[kPlanMaxSub];
+  bool ready = false;
+};
+
+PlanStreams* plan_streams() {
+  static PlanStreams table[64];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  PlanStreams& ps = table[dev];
+  if (!ps.ready) {
+    for (int i = 0; i < kPlanMaxSub; ++i) {
+      if (cudaStreamCreateWithFlags(&ps.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&ps.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&ps.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ps.ready = true;
+  }
+  return &ps;
+}
+
+long long plan_unit(const swm_rollout_t* cfg) {  // environments that must stay in one launch
+  const bool perturbed = cfg->policy_mode == SWM_POLICY_PHILOX || cfg->policy_mode == SWM_POLICY_DELTAS;
+  return (long long)cfg->rollouts_per_policy * (perturbed ? 2 : 1);
+}
+
+// contiguous sub-batches of whole units; cut[i] .. cut[i+1]
+int plan_cuts(long long B, long long unit, int n_sub, long long* cut) {
+  const long long groups = B / unit;
+  if (n_sub > groups) n_sub = (int)groups;
+  if (n_sub < 1) n_sub = 1;
+  for (int i = 0; i <= n_sub; ++i) cut[i] = unit * ((groups * i) / n_sub);
+  return n_sub;
+}
+
+bool plan_feasible(const swm_rollout_t* cfg, const RolloutFlags& f, int n_sub, int chunk) {
+  if (n_sub < 1 || n_sub > kPlanMaxSub || chunk < 64 || chunk % 64 != 0) return false;
+  if (!cfg->final_state || cfg->trajectory || f.screen || cfg->H <= chunk) return false;
+  const long long unit = plan_unit(cfg);
+  if (cfg->B % unit != 0) return false;
+  if (cfg->init_state && cfg->init_state_count != cfg->B) {
+    long long cut[kPlanMaxSub + 1];
+    const int ns = plan_cuts(cfg->B, unit, n_sub, cut);
+    for (int i = 0; i < ns; ++i)
+      if (cut[i] % cfg->init_state_count != 0) return false;  // e % count must not change with the offset
+  }
+  return true;
+}
+
+Plan choose_plan(int n, const swm_rollout_t* cfg, const RolloutFlags& f, int kernel, cudaStream_t st) {
+  Plan p;
+  if (kernel != SWM_KERNEL_THREAD || cfg->schedule_sub < 0) return p;
+  if (cfg->schedule_sub > 0) {  // forced by the caller
+    if (plan_feasible(cfg, f, cfg->schedule_sub, cfg->schedule_chunk)) { p.n_sub = cfg->schedule_sub; p.chunk = cfg->schedule_chunk; }
+    return p;
+  }
+  // AUTO: only where it was measured to pay (tools/chunk_sweep.py, profiles/r02_chunk_sweep.txt): between 3 and 4
+  // warps per sub-partition, kernels that keep >= 2 warps per sub-partition resident (n <= 5)
+  if (n > 5) return p;
+  const double w = (double)((cfg->B + 31) / 32) / (4.0 * sm_count_cached());
+  if (w <= 3.05 || w >= 3.95) return p;
+  // Fine chunks balance best (16 x 64: +20 % for the fixed-action kernel) but are 256 launches per rollout: that
+  // only pays when the caller is capturing a CUDA graph (replay has no per-launch host cost).  Enqueued
+  // eagerly -- and for policy kernels, which regenerate their policy in every launch -- 8 x 256 (+14 %).
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool capturing = cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive;
+  const bool fine = capturing && !f.linear;
+  const int n_sub = fine ? 16 : 8, chunk = fine ? 64 : 256;
+  if (plan_feasible(cfg, f, n_sub, chunk)) { p.n_sub = n_sub; p.chunk = chunk; }
+  return p;
+}
+
+long long plan_stats_rows(const swm_rollout_t* cfg, const Plan& p) {
+  long long cut[kPlanMaxSub + 1];
+  const int ns = plan_cuts(cfg->B, plan_unit(cfg), p.n_sub, cut);
+  long long rows = 0;
+  for (int i = 0; i < ns; ++i) rows += (cut[i + 1] - cut[i] + kRolloutBlock - 1) / kRolloutBlock;
+  return rows * ((cfg->H + p.chunk - 1) / p.chunk);
+}
+
+int launch_thread_kernel(int n, const RolloutArgs& a, const RolloutFlags& f, cudaStream_t st) {
+#define CALL(K) launch_rollout_n<K>(a, f, st)
+  SWM_DISPATCH_N(n, CALL)
+#undef CALL
+}
+
+int launch_planned(int n, const swm_rollout_t* cfg, const RolloutArgs& a0, const RolloutFlags& f, const Plan& p,
+                   cudaStream_t st) {
+  PlanStreams* ps = plan_streams();
+  if (!ps) return SWM_ERR_CUDA;
+  const int NO = 2 * n + 2, NA = n - 1, WS = NA * NO;
+  const long long unit = plan_unit(cfg);
+  long long cut[kPlanMaxSub + 1];
+  const int ns = plan_cuts(a0.B, unit, p.n_sub, cut);
+  const bool perturbed = cfg->policy_mode == SWM_POLICY_PHILOX || cfg->policy_mode == SWM_POLICY_DELTAS;
+  if (cudaEventRecord(ps->fork, st) != cudaSuccess) return SWM_ERR_CUDA;
+  for (int i = 0; i < ns; ++i)
+    if (cudaStreamWaitEvent(ps->s[i], ps->fork, 0) != cudaSuccess) return SWM_ERR_CUDA;
+  long long row = 0;
+  int rc = SWM_OK;
+  for (int t0 = 0, c = 0; t0 < a0.H && rc == SWM_OK; t0 += p.chunk, ++c) {
+    for (int i = 0; i < ns && rc == SWM_OK; ++i) {
+      const long long lo = cut[i], Bs = cut[i + 1] - cut[i];
+      RolloutArgs a = a0;
+      a.B = Bs;
+      a.H = (a0.H - t0 < p.chunk) ? a0.H - t0 : p.chunk;
+      a.returns = a0.returns + lo;
+      a.final_state = a0.final_state + lo * NO;
+      if (a0.actions) a.actions = a0.actions + lo * NA;
+      if (f.linear) {
+        const long long pol = lo / a0.R;  // first policy of this sub-batch
+        if (cfg->policy_mode == SWM_POLICY_EXPLICIT) a.policies = a0.policies + pol * WS;
+        if (perturbed) a.dir0 = a0.dir0 + (unsigned int)(pol >> 1);
+        if (a0.deltas) a.deltas = a0.deltas + (pol >> 1) * WS;
+        if (a0.dir_mask) a.dir_mask = a0.dir_mask + (pol >> 1);
+      }
+      if (c == 0) {
+        if (a0.init_state && a0.init_count == a0.B) { a.init_state = a0.init_state + lo * NO; a.init_count = Bs; }
+      } else {
+        a.init_state = a.final_state;  // continue from the state the previous chunk left
+        a.init_count = Bs;
+        a.init_perturb = 0.0;
+        a.accumulate = 1;
+      }
+      if (a0.stats_partial) {
+        a.stats_partial = a0.stats_partial + row * 2 * NO;
+        row += (Bs + kRolloutBlock - 1) / kRolloutBlock;
+      }
+      rc = launch_thread_kernel(n, a, f, ps->s[i]);
+    }
+  }
+  for (int i = 0; i < ns; ++i) {
+    if (cudaEventRecord(ps->join[i], ps->s[i]) != cudaSuccess || cudaStreamWaitEvent(st, ps->join[i], 0) != cudaSuccess)
+      return SWM_ERR_CUDA;
+  }
+  return rc;
+}
+
+}  // namespace
+
+extern "C" int swm_rollout_schedule(const swm_params_t* params, const swm_rollout_t* cfg, void* stream, int* n_sub,
+                                    int* chunk) {
+  RolloutArgs a;
+  RolloutFlags f;
+  const int rc = build_rollout_args(params, cfg, a, f);
+  if (rc != SWM_OK) return rc;
+  const int kernel = choose_kernel(params->n, cfg, a, f);
+  if (kernel < 0) return kernel;
+  const Plan p = choose_plan(params->n, cfg, f, kernel, (cudaStream_t)stream);
+  if (n_sub) *n_sub = p.n_sub;
+  if (chunk) *chunk = p.chunk;
+  return SWM_OK;
+}
+
+extern "C" int64_t swm_rollout_stats_blocks(const swm_params_t* params, const swm_rollout_t* cfg, void* stream) {
   if (!cfg || cfg->B < 1) return 0;
-  // the row count only depends on the kernel choice, which never looks at the output pointers
+  // the row count depends on the kernel and the schedule swm_rollout will choose, which never look at the
+  // statistics pointers themselves
   swm_rollout_t probe = *cfg;
   static double dummy;
   probe.stats_partial = &dummy;
-  if (swm_rollout_kernel_choice(params, &probe) == SWM_KERNEL_LANES) {
+  RolloutArgs a;
+  RolloutFlags f;
+  if (build_rollout_args(params, &probe, a, f) != SWM_OK) return 0;
+  const int kernel = choose_kernel(params->n, &probe, a, f);
+  if (kernel == SWM_KERNEL_LANES) {
     const int per_warp = 32 / lane_split_lanes(params->n);
     return (cfg->B + per_warp - 1) / per_warp;
   }
+  const Plan p = choose_plan(params->n, &probe, f, kernel, (cudaStream_t)stream);
+  if (p.n_sub > 0) return plan_stats_rows(&probe, p);
   return (cfg->B + kRolloutBlock - 1) / kRolloutBlock;
 }
 
@@ -301,9 +481,10 @@ extern "C" int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg,
     SWM_DISPATCH_N(params->n, CALL)
 #undef CALL
   }
-#define CALL(K) launch_rollout_n<K>(a, f, st)
-  SWM_DISPATCH_N(params->n, CALL)
-#undef CALL
+  const Plan p = choose_plan(params->n, cfg, f, kernel, st);
+  if (cfg->schedule_sub > 0 && p.n_sub == 0) return SWM_ERR_UNSUPPORTED;  // a forced schedule that cannot run
+  if (p.n_sub > 0) return note_launch(launch_planned(params->n, cfg, a, f, p, st));
+  return launch_thread_kernel(params->n, a, f, st);
 }
 
 // Layout self-check for language bindings: sizes of the ABI structs as this build sees them.

@@ -122,7 +122,7 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
             seed=0, iteration=0, iteration_dev=None, dir0=0, delta_dist=DELTA_PM1, rollouts_per_policy=1, mean=None,
             inv_sigma=None, clip_actions=False, init_state=None, want_final=False,
             want_trajectory=False, stats_pivot=None, screen=None, out=None, device=None,
-            accumulate_returns=False, kernel=0):
+            accumulate_returns=False, kernel=0, schedule=None):
     """One fused H-step rollout of B environments (swm_rollout).
 
     Exactly one of
@@ -137,6 +137,8 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
     tensors (returns, final_state, trajectory, stats_partial) to stay allocation-free in loops.
     kernel: _lib.KERNEL_AUTO (chosen from B, n and the SM count) / KERNEL_THREAD (one thread per
     environment) / KERNEL_LANES (one environment over 4/8/16 lanes; small batches).
+    schedule: None = the library decides between one plain launch and a chunked schedule (needs want_final;
+    swm_rollout_t.schedule_sub); "plain" = always one launch; (n_sub, chunk) = forced.
     """
     _lib.require_cuda()
     n = params.n
@@ -182,6 +184,10 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
     cfg.clip_actions = int(bool(clip_actions))
     cfg.accumulate_returns = int(bool(accumulate_returns))
     cfg.kernel = int(kernel)
+    if schedule == "plain":
+        cfg.schedule_sub = -1
+    elif schedule is not None:
+        cfg.schedule_sub, cfg.schedule_chunk = int(schedule[0]), int(schedule[1])
     cfg.screen.enabled = int(screen is not None)  # before swm_rollout_stats_blocks: it decides the kernel
     cfg.nu = float(nu)
     cfg.init_perturb = float(init_perturb)
@@ -219,7 +225,8 @@ def rollout(params, H, *, B=None, variant=GYM, actions=None, policies=None, base
         cfg.trajectory = res.trajectory.data_ptr()
     if stats_pivot is not None:
         stats_pivot = _lib.f64(stats_pivot, (no,)).contiguous()
-        nb = _lib.lib().swm_rollout_stats_blocks(ctypes.byref(params), ctypes.byref(cfg))
+        with torch.cuda.device(dev):
+            nb = _lib.lib().swm_rollout_stats_blocks(ctypes.byref(params), ctypes.byref(cfg), _lib.stream_ptr())
         res.stats_partial = buf("stats_partial", (nb, 2, no))
         res.stats_blocks = nb
         res.samples = float(B) * float(H)
@@ -333,7 +340,7 @@ class ChunkedRollout:
                             init_state=None if c == 0 else self.state[lo:hi],
                             init_perturb=init_perturb if c == 0 else 0.0, want_final=True,
                             stats_pivot=self.stats_pivot, accumulate_returns=c > 0, out=out,
-                            kernel=_lib.KERNEL_THREAD, **src, **call)
+                            kernel=_lib.KERNEL_THREAD, schedule="plain", **src, **call)
         for st in self.streams:
             cur.wait_stream(st)
         res = RolloutResult()

@@ -348,3 +348,61 @@ def test_chunked_rollout_equals_single_launch(S, case):
                 np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-13)
     with pytest.raises(ValueError):
         S.ops.ChunkedRollout(p, H, B=B, chunk=100, **kw, **extra)
+
+
+def test_native_schedule_equals_plain_launch(S):
+    """swm_rollout's own chunked schedule (sub-batches x 64-step chunks on internal streams, chosen by the
+    library for batches that leave 3-4 warps per SM sub-partition, or forced through schedule_sub / _chunk):
+    final states bit-identical to one plain launch, returns equal to the rounding of the partial sums, V2
+    moments to 1e-12; unschedulable requests fail loudly; the query entry point reports the choice."""
+    import ctypes
+    rng = np.random.default_rng(5)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    # auto: fixed actions, n = 3, 3.46 warps per sub-partition on a 148-SM part
+    B = int(3.46 * 4 * sms * 32) // 64 * 64
+    p = S.make_params(n=3)
+    ac = _cuda(rng.uniform(-5, 5, (B, 2)))
+    auto = S.ops.rollout(p, 300, actions=ac, want_final=True)
+    plain = S.ops.rollout(p, 300, actions=ac, want_final=True, schedule="plain")
+    assert torch.equal(auto.final_state, plain.final_state)
+    np.testing.assert_allclose(auto.returns.cpu().numpy(), plain.returns.cpu().numpy(), rtol=1e-12, atol=1e-13)
+    cfg = S._lib.SwmRollout()
+    cfg.policy_mode, cfg.H, cfg.B, cfg.rollouts_per_policy = 0, 300, B, 1
+    cfg.actions, cfg.returns, cfg.final_state = ac.data_ptr(), auto.returns.data_ptr(), auto.final_state.data_ptr()
+    ns, ch = ctypes.c_int(-1), ctypes.c_int(-1)
+    assert S._lib.lib().swm_rollout_schedule(ctypes.byref(p), ctypes.byref(cfg), None, ctypes.byref(ns), ctypes.byref(ch)) == 0
+    assert (ns.value, ch.value) == (8, 256)    # enqueued eagerly: few launches; 16 x 64 while capturing a graph
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        captured = S.ops.rollout(p, 300, actions=ac, want_final=True)
+        assert S._lib.lib().swm_rollout_schedule(ctypes.byref(p), ctypes.byref(cfg), S._lib.stream_ptr(), ctypes.byref(ns),
+                                                 ctypes.byref(ch)) == 0
+    assert (ns.value, ch.value) == (16, 64)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured.final_state, plain.final_state)
+    cfg.final_state = None   # no chaining buffer: plain
+    assert S._lib.lib().swm_rollout_schedule(ctypes.byref(p), ctypes.byref(cfg), None, ctypes.byref(ns), ctypes.byref(ch)) == 0
+    assert ns.value == 0
+    # forced: V2 Philox policies with moments, R rollouts per policy from R start states, dir_mask, n = 5
+    n, R, D, H = 5, 4, 24, 200
+    p = S.make_params(n=n)
+    no = 2 * n + 2
+    kw = dict(B=2 * D * R, base_policy=_cuda(rng.uniform(-1, 1, (n - 1) * no) * 0.1), nu=0.05, seed=4, iteration=2, dir0=3,
+              rollouts_per_policy=R, init_state=_cuda(rand_states(rng, n, R, scale=0.3)), init_perturb=1e-2,
+              mean=_cuda(rng.normal(size=no) * 0.05), inv_sigma=_cuda(rng.uniform(.5, 2, no)),
+              stats_pivot=S.ops.reset_state(n), want_final=True, kernel=S.KERNEL_THREAD,
+              dir_mask=torch.tensor([1, 1, 0, 1] * 6, dtype=torch.int32, device="cuda"))
+    plain = S.ops.rollout(p, H, schedule="plain", **kw)
+    for sched in ((3, 64), (5, 128), (16, 64)):
+        got = S.ops.rollout(p, H, schedule=sched, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.nan_to_num(got.final_state), torch.nan_to_num(plain.final_state)), sched
+        np.testing.assert_allclose(got.returns.cpu().numpy(), plain.returns.cpu().numpy(), rtol=1e-12, atol=1e-13)
+        a = S.ops.stats_finalize(got.stats_partial, got.samples, kw["stats_pivot"]).cpu().numpy()
+        b = S.ops.stats_finalize(plain.stats_partial, plain.samples, kw["stats_pivot"]).cpu().numpy()
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-13)
+    with pytest.raises(S.SwimmerLibError):   # trajectories cannot be chunked
+        S.ops.rollout(p, H, schedule=(4, 64), want_trajectory=True, **kw)
+    with pytest.raises(S.SwimmerLibError):   # chunk must be a multiple of 64
+        S.ops.rollout(p, H, schedule=(4, 100), **kw)
