@@ -60,6 +60,10 @@ __device__ __forceinline__ double opaque(double x) {
   return x;
 }
 constexpr int kKeepTsTc = 7;
+#ifndef SWM_FACT_SMEM_RHS_ONLY
+#define SWM_FACT_SMEM_RHS_ONLY 1
+#endif
+constexpr bool kFactSmemRhsOnly = SWM_FACT_SMEM_RHS_ONLY != 0;
 constexpr int kRegLuMax = 90;  // rlglue variant: largest augmented system (doubles) factorised in registers (n <= 7)
 
 // ---------------------------------------------------------------------------------------------
@@ -73,11 +77,15 @@ constexpr int kRegLuMax = 90;  // rlglue variant: largest augmented system (doub
 //   thdd_i = 3 n_i.(g_i + g_{i+1}) + tau~_i,    Gdd = l/(2n) sum_i psi_i
 // s[i] = sin(th_i), c[i] = cos(th_i); ut has N-1 entries (already scaled by u_scale).
 // ---------------------------------------------------------------------------------------------
-template <int N>
+// FS: where the factorisation (5 doubles per joint) lives between the forward and the backward sweep:
+// 0 = registers, > 0 = shared memory, element k of this thread at fs[k * FS] (FS = threads per CTA).  Long
+// chains (n >= 8) keep 45 doubles there instead of 90 registers that the 255-register limit cannot hold.
+template <int N, int FS = 0>
 __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&s)[N],
                                                   const double (&c)[N], double gdx, double gdy,
                                                   const double (&thd)[N], const double* ut,
-                                                  double& psx, double& psy, double (&thdd)[N]) {
+                                                  double& psx, double& psy, double (&thdd)[N],
+                                                  double* fs = nullptr) {
   // Outputs: thdd, and (psx, psy) = sum_i psi_i; the caller scales it (Gdd = gdd_c * sum).
   // Streaming formulation: apart from the factorisation (5 doubles per joint) everything is a
   // rolling value, so the live state is O(N) with a small constant (registers, no local memory).
@@ -101,8 +109,14 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
   // pass 1 -- per segment: friction, right-hand sides, and the forward block elimination of the
   // joint between segment i-1 and i.
   constexpr int J = N - 1;
-  double Xa[J > 0 ? J : 1], Xb[J > 0 ? J : 1], Xd[J > 0 ? J : 1];  // inverse pivot blocks
-  double rx[J > 0 ? J : 1], ry[J > 0 ? J : 1];                     // eliminated right-hand sides
+  constexpr int JR = (FS == 0 && J > 0) ? J : 1;
+  // FS > 0 with kFactSmemRhsOnly: only the eliminated right-hand sides (2 doubles per joint) go to shared
+  // memory, the inverse pivot blocks stay in registers -- enough to remove the last spills of n = 10 at 40 % of
+  // the shared-memory traffic
+  constexpr int JX = ((FS == 0 || kFactSmemRhsOnly) && J > 0) ? J : 1;
+  double Xa[JX], Xb[JX], Xd[JX];  // inverse pivot blocks
+  double rx[JR], ry[JR];          // eliminated right-hand sides
+  double pXa = 0.0, pXb = 0.0, pXd = 0.0, prx = 0.0, pry = 0.0;  // FS > 0: the previous joint's values (registers)
   double ax = sx, ay = sy;          // velocity of the joint at the head of segment i
   double sumx = 0.0, sumy = 0.0;    // sum_i F_i n_i
   double Bpx = 0.0, Bpy = 0.0;      // B_{i-1}
@@ -133,22 +147,36 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
       double r0 = Ax - Bpx, r1 = Ay - Bpy;
       if (i >= 2) {
         const double qa = fma(3.0, ssp, -1.0), qb = -3.0 * scp, qd = 1.0 - qa;  // Q_{i-1}
-        const double t00 = fma(qa, Xa[i - 2], qb * Xb[i - 2]);
-        const double t01 = fma(qa, Xb[i - 2], qb * Xd[i - 2]);
-        const double t10 = fma(qb, Xa[i - 2], qd * Xb[i - 2]);
-        const double t11 = fma(qb, Xb[i - 2], qd * Xd[i - 2]);
+        const double xa = FS ? pXa : Xa[FS ? 0 : i - 2], xb = FS ? pXb : Xb[FS ? 0 : i - 2];
+        const double xd = FS ? pXd : Xd[FS ? 0 : i - 2];
+        const double rpx = FS ? prx : rx[FS ? 0 : i - 2], rpy = FS ? pry : ry[FS ? 0 : i - 2];
+        const double t00 = fma(qa, xa, qb * xb);
+        const double t01 = fma(qa, xb, qb * xd);
+        const double t10 = fma(qb, xa, qd * xb);
+        const double t11 = fma(qb, xb, qd * xd);
         pa = fma(-t01, qb, fma(-t00, qa, pa));
         pb = fma(-t01, qd, fma(-t00, qb, pb));
         pd = fma(-t11, qd, fma(-t10, qb, pd));
-        r0 = fma(-t01, ry[i - 2], fma(-t00, rx[i - 2], r0));
-        r1 = fma(-t11, ry[i - 2], fma(-t10, rx[i - 2], r1));
+        r0 = fma(-t01, rpy, fma(-t00, rpx, r0));
+        r1 = fma(-t11, rpy, fma(-t10, rpx, r1));
       }
       const double idet = fast_rcp(fma(pa, pd, -pb * pb));
-      Xa[i - 1] = pd * idet;
-      Xb[i - 1] = -pb * idet;
-      Xd[i - 1] = pa * idet;
-      rx[i - 1] = r0;
-      ry[i - 1] = r1;
+      if (FS && kFactSmemRhsOnly) {
+        pXa = pd * idet; pXb = -pb * idet; pXd = pa * idet; prx = r0; pry = r1;
+        Xa[JX > 1 ? i - 1 : 0] = pXa; Xb[JX > 1 ? i - 1 : 0] = pXb; Xd[JX > 1 ? i - 1 : 0] = pXd;
+        double* f = fs + (size_t)(2 * (i - 1)) * FS;
+        f[0] = r0; f[FS] = r1;
+      } else if (FS) {
+        pXa = pd * idet; pXb = -pb * idet; pXd = pa * idet; prx = r0; pry = r1;
+        double* f = fs + (size_t)(5 * (i - 1)) * FS;
+        f[0] = pXa; f[FS] = pXb; f[2 * FS] = pXd; f[3 * FS] = r0; f[4 * FS] = r1;
+      } else {
+        Xa[FS ? 0 : i - 1] = pd * idet;
+        Xb[FS ? 0 : i - 1] = -pb * idet;
+        Xd[FS ? 0 : i - 1] = pa * idet;
+        rx[FS ? 0 : i - 1] = r0;
+        ry[FS ? 0 : i - 1] = r1;
+      }
     }
     if (i <= N - 2) {
       // B_i = psi_i + w^_i = (F + tau~) n_i - thd^2 p_i
@@ -165,14 +193,25 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
   double gnx = 0.0, gny = 0.0;  // g_{j+1}
 #pragma unroll
   for (int j = J; j >= 1; --j) {
-    double y0 = rx[j - 1], y1 = ry[j - 1];
+    double y0, y1, xa, xb, xd;
+    if (FS && kFactSmemRhsOnly) {
+      const double* f = fs + (size_t)(2 * (j - 1)) * FS;
+      xa = Xa[JX > 1 ? j - 1 : 0]; xb = Xb[JX > 1 ? j - 1 : 0]; xd = Xd[JX > 1 ? j - 1 : 0];
+      y0 = f[0]; y1 = f[FS];
+    } else if (FS) {
+      const double* f = fs + (size_t)(5 * (j - 1)) * FS;
+      xa = f[0]; xb = f[FS]; xd = f[2 * FS]; y0 = f[3 * FS]; y1 = f[4 * FS];
+    } else {
+      xa = Xa[FS ? 0 : j - 1]; xb = Xb[FS ? 0 : j - 1]; xd = Xd[FS ? 0 : j - 1];
+      y0 = rx[FS ? 0 : j - 1]; y1 = ry[FS ? 0 : j - 1];
+    }
     if (j < J) {
       const double qa = fma(3.0, s[j] * s[j], -1.0), qb = -3.0 * (s[j] * c[j]), qd = 1.0 - qa;
       y0 = fma(-qb, gny, fma(-qa, gnx, y0));
       y1 = fma(-qd, gny, fma(-qb, gnx, y1));
     }
-    const double gjx = fma(Xa[j - 1], y0, Xb[j - 1] * y1);
-    const double gjy = fma(Xb[j - 1], y0, Xd[j - 1] * y1);
+    const double gjx = fma(xa, y0, xb * y1);
+    const double gjy = fma(xb, y0, xd * y1);
     // segment j lies between joints j and j+1
     const double ex = (j == J) ? gjx : gjx + gnx, ey = (j == J) ? gjy : gjy + gny;
     thdd[j] = fma(3.0, fma(c[j], ey, -s[j] * ex), thdd[j]);
@@ -475,13 +514,13 @@ __device__ __forceinline__ double swimmer_step(const Phys& P, double& gdx, doubl
 // step and advanced by the rotation of the angle increment h*thd instead of being re-evaluated.
 // `resync` (warp-uniform; the rollout kernel sets it every 64th step) or an increment above 1/8 rad
 // on any segment re-evaluates them exactly from th.  ut = torques already scaled by P.u_scale.
-template <int N>
+template <int N, int FS = 0>
 __device__ __forceinline__ void gym_step_tracked(const Phys& P, double& gdx, double& gdy,
                                                  double (&th)[N], double (&thd)[N],
                                                  double (&s)[N], double (&c)[N],
-                                                 const double* ut, bool resync) {
+                                                 const double* ut, bool resync, double* fs = nullptr) {
   double psx, psy, thdd[N];
-  gym_accelerations<N>(P, s, c, gdx, gdy, thd, ut, psx, psy, thdd);
+  gym_accelerations<N, FS>(P, s, c, gdx, gdy, thd, ut, psx, psy, thdd, fs);
   gdx = fma(P.h_gdd_c, psx, gdx);
   gdy = fma(P.h_gdd_c, psy, gdy);
   double d[N];

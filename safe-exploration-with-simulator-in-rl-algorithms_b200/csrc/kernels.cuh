@@ -22,6 +22,14 @@ constexpr int kRolloutBlock = 64;  // threads per CTA of the rollout kernel (2 w
 constexpr int kRegPolicyMax = 32;  // largest policy (doubles) kept in registers: n <= 4
 constexpr int kRegStatsMaxObs = 16; // V2 moment accumulators stay in registers up to n = 7; above, they
                                     // live in shared memory (one column per thread)
+#ifndef SWM_FACT_SMEM_MIN_N
+#define SWM_FACT_SMEM_MIN_N 8       // from this chain length on, the joint factorisation (5 doubles per joint) of
+#endif                              // the gym dynamics is kept in shared memory between its two sweeps
+constexpr int kFactSmemMinN = SWM_FACT_SMEM_MIN_N;
+template <int N, int VARIANT> struct FactSmem {
+  static constexpr bool on = (VARIANT == 0) && (N >= kFactSmemMinN);
+  static constexpr int doubles = on ? (kFactSmemRhsOnly ? 2 : 5) * (N - 1) : 0;  // per thread
+};
 
 // Where the per-environment policy lives during a rollout.
 enum WMode {
@@ -286,6 +294,14 @@ rollout_kernel(const RolloutArgs a) {
   double s1[STATS_REG ? NO : 1], s2[STATS_REG ? NO : 1];
   // STATS_SMEM: accumulator j of this thread at sS[j * kRolloutBlock], j < 2*NO, after the policies
   double* sS = smem + tid;
+  // gym dynamics of long chains: factorisation scratch, element k of this thread at sF[k * kRolloutBlock]
+  constexpr int FS = FactSmem<N, VARIANT>::on ? kRolloutBlock : 0;
+  double* sF = smem + tid;
+  if (FS) {
+    if (WMODE == W_SMEM_THREAD) sF += WS * kRolloutBlock;
+    if (WMODE == W_SMEM_GROUP) sF += WS * (kRolloutBlock / 32);
+    if (STATS_SMEM) sF += 2 * NO * kRolloutBlock;
+  }
   if (STATS_SMEM) {
     if (WMODE == W_SMEM_THREAD) sS += WS * kRolloutBlock;
     if (WMODE == W_SMEM_GROUP) sS += WS * (kRolloutBlock / 32);
@@ -362,7 +378,7 @@ rollout_kernel(const RolloutArgs a) {
       double sut[NA > 0 ? NA : 1], sgddx, sgddy, sthdd[N], sthd[N];
 #pragma unroll
       for (int k = 0; k < NA; ++k) sut[k] = u[k] * a.sim.u_scale;
-      gym_accelerations<N>(a.sim, sn, cs, gdx, gdy, thd, sut, sgddx, sgddy, sthdd);
+      gym_accelerations<N, FS>(a.sim, sn, cs, gdx, gdy, thd, sut, sgddx, sgddy, sthdd, sF);
 #pragma unroll
       for (int i = 0; i < N; ++i) sthd[i] = fma(a.sim.h, sthdd[i], thd[i]);
       if (!(cost_max_abs_thd<N>(sthd) <= a.sim_thresh)) {
@@ -383,7 +399,7 @@ rollout_kernel(const RolloutArgs a) {
     if (VARIANT == 0) {
       // reward_t = Gdot_t . direction (remy_swimmer_env.py:238-243); the two components are summed
       // separately and dotted with the direction once, after the loop
-      gym_step_tracked<N>(a.real, gdx, gdy, th, thd, sn, cs, ut, (t & 63) == 63);
+      gym_step_tracked<N, FS>(a.real, gdx, gdy, th, thd, sn, cs, ut, (t & 63) == 63, sF);
       sgx += gdx;
       sgy += gdy;
     } else {

@@ -29,6 +29,7 @@ static int launch_rollout_one(const RolloutArgs& a, cudaStream_t st) {
   if (WMODE == W_SMEM_THREAD) smem = sizeof(double) * WS * kRolloutBlock;
   if (WMODE == W_SMEM_GROUP) smem = sizeof(double) * WS * (kRolloutBlock / 32);
   if (STATS && (2 * N + 2) > kRegStatsMaxObs) smem += sizeof(double) * 2 * (2 * N + 2) * kRolloutBlock;
+  smem += sizeof(double) * FactSmem<N, VARIANT>::doubles * kRolloutBlock;
   auto kern = rollout_kernel<N, VARIANT, WMODE, NORM, STATS, SCREEN>;
   // dynamic + static shared memory (s_mu, s_piv, the moment reduction scratch: < 2 KB) above the default
   // 48 KB limit needs the opt-in attribute
