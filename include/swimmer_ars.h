@@ -78,9 +78,11 @@ typedef enum {
 typedef enum {
   SWM_KERNEL_AUTO = 0,
   SWM_KERNEL_THREAD = 1, /* one thread = one environment (throughput: BASELINE configs 2 and 5) */
-  SWM_KERNEL_LANES = 2   /* one environment spread over 4/8/16 lanes, lane = segment (latency: the 2,048-env
+  SWM_KERNEL_LANES = 2,  /* one environment spread over 4/8/16 lanes, lane = segment (latency: the 2,048-env
                             ARS iteration of config 3, the 512-env safe-exploration rollouts of config 4);
                             gym dynamics without per-step screening / clipping, else SWM_ERR_UNSUPPORTED */
+  SWM_KERNEL_LANES2 = 3  /* LANES cut into two warps per lane group (main warp + factorisation warp on separate
+                            SM sub-partitions): batches so small that sub-partitions would otherwise idle */
 } swm_rollout_kernel;
 
 /* Distribution of the Philox perturbations. */

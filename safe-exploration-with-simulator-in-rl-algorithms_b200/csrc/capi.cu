@@ -180,7 +180,7 @@ int build_rollout_args(const swm_params_t* params, const swm_rollout_t* cfg, Rol
   if (!params_ok(params) || !cfg) return SWM_ERR_BAD_ARG;
   if (cfg->B < 0 || cfg->H < 0 || cfg->rollouts_per_policy < 1) return SWM_ERR_BAD_ARG;
   if (cfg->variant != SWM_DYN_GYM && cfg->variant != SWM_DYN_RLGLUE) return SWM_ERR_BAD_ARG;
-  if (cfg->kernel < SWM_KERNEL_AUTO || cfg->kernel > SWM_KERNEL_LANES) return SWM_ERR_BAD_ARG;
+  if (cfg->kernel < SWM_KERNEL_AUTO || cfg->kernel > SWM_KERNEL_LANES2) return SWM_ERR_BAD_ARG;
   if (cfg->B > (int64_t)kRolloutBlock * 0x7fffffffLL) return SWM_ERR_BAD_ARG;
   memset(&a, 0, sizeof(a));
   f.variant = cfg->variant;
@@ -251,7 +251,7 @@ constexpr double kLaneSplitMaxWarpsPerSmsp = 2.0;
 
 int choose_kernel(int n, const swm_rollout_t* cfg, const RolloutArgs& a, const RolloutFlags& f) {
   const bool ok = lane_split_supported(a, f);
-  if (cfg->kernel == SWM_KERNEL_LANES) return ok ? SWM_KERNEL_LANES : SWM_ERR_UNSUPPORTED;
+  if (cfg->kernel == SWM_KERNEL_LANES || cfg->kernel == SWM_KERNEL_LANES2) return ok ? cfg->kernel : SWM_ERR_UNSUPPORTED;
   if (cfg->kernel == SWM_KERNEL_THREAD || !ok || n > 7) return SWM_KERNEL_THREAD;
   const int per_warp = 32 / lane_split_lanes(n);
   const double warps = (double)((cfg->B + per_warp - 1) / per_warp);
@@ -450,7 +450,7 @@ extern "C" int64_t swm_rollout_stats_blocks(const swm_params_t* params, const sw
   RolloutFlags f;
   if (build_rollout_args(params, &probe, a, f) != SWM_OK) return 0;
   const int kernel = choose_kernel(params->n, &probe, a, f);
-  if (kernel == SWM_KERNEL_LANES) {
+  if (kernel == SWM_KERNEL_LANES || kernel == SWM_KERNEL_LANES2) {
     const int per_warp = 32 / lane_split_lanes(params->n);
     return (cfg->B + per_warp - 1) / per_warp;
   }
@@ -476,8 +476,8 @@ extern "C" int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg,
   const int kernel = choose_kernel(params->n, cfg, a, f);
   if (kernel < 0) return kernel;
   cudaStream_t st = (cudaStream_t)stream;
-  if (kernel == SWM_KERNEL_LANES) {
-#define CALL(K) launch_lane_rollout_n<K>(a, f, st)
+  if (kernel == SWM_KERNEL_LANES || kernel == SWM_KERNEL_LANES2) {
+#define CALL(K) launch_lane_rollout_n<K>(a, f, kernel == SWM_KERNEL_LANES2, st)
     SWM_DISPATCH_N(params->n, CALL)
 #undef CALL
   }

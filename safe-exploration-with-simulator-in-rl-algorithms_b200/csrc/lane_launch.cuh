@@ -1,7 +1,7 @@
 // Host-side dispatch of the lane-split rollout kernel for one segment count N (see lane_rollout.cuh).
 // Each lane_nK.cu translation unit instantiates launch_lane_rollout_n<K>.
 #pragma once
-#include "lane_rollout.cuh"
+#include "lane2_rollout.cuh"
 #include "launch.cuh"
 
 namespace swm {
@@ -17,29 +17,31 @@ inline bool lane_split_supported(const RolloutArgs& a, const RolloutFlags& f) {
   return !(f.stats && !f.norm);
 }
 
-template <int N> int launch_lane_rollout_n(const RolloutArgs& a, const RolloutFlags& f, cudaStream_t st);
+// two_warps: the warp-specialised form (lane2_rollout.cuh: main warp + factorisation warp per lane group)
+template <int N> int launch_lane_rollout_n(const RolloutArgs& a, const RolloutFlags& f, bool two_warps, cudaStream_t st);
 
 #ifdef SWM_INSTANTIATE_LANE_N
 
 template <int N, bool LINEAR, bool NORM, bool STATS>
-static int launch_lane_one(const RolloutArgs& a, cudaStream_t st) {
+static int launch_lane_one(const RolloutArgs& a, bool two_warps, cudaStream_t st) {
   constexpr int G = LaneSplit<N>::G;
   const long long blocks = (a.B + G - 1) / G;
   if (blocks > 0x7fffffffLL) return SWM_ERR_BAD_ARG;
-  lane_rollout_kernel<N, LINEAR, NORM, STATS><<<(unsigned)blocks, kLaneBlock, 0, st>>>(a);
+  if (two_warps) lane2_rollout_kernel<N, LINEAR, NORM, STATS><<<(unsigned)blocks, kLane2Block, 0, st>>>(a);
+  else lane_rollout_kernel<N, LINEAR, NORM, STATS><<<(unsigned)blocks, kLaneBlock, 0, st>>>(a);
   return cudaPeekAtLastError() == cudaSuccess ? SWM_OK : SWM_ERR_CUDA;
 }
 
 template <int N>
-int launch_lane_rollout_n(const RolloutArgs& a, const RolloutFlags& f, cudaStream_t st) {
+int launch_lane_rollout_n(const RolloutArgs& a, const RolloutFlags& f, bool two_warps, cudaStream_t st) {
   if (!lane_split_supported(a, f)) return SWM_ERR_UNSUPPORTED;
-  if (!f.linear) return launch_lane_one<N, false, false, false>(a, st);
-  if (f.norm && f.stats) return launch_lane_one<N, true, true, true>(a, st);
-  if (f.norm) return launch_lane_one<N, true, true, false>(a, st);
-  return launch_lane_one<N, true, false, false>(a, st);
+  if (!f.linear) return launch_lane_one<N, false, false, false>(a, two_warps, st);
+  if (f.norm && f.stats) return launch_lane_one<N, true, true, true>(a, two_warps, st);
+  if (f.norm) return launch_lane_one<N, true, true, false>(a, two_warps, st);
+  return launch_lane_one<N, true, false, false>(a, two_warps, st);
 }
 
-template int launch_lane_rollout_n<SWM_INSTANTIATE_LANE_N>(const RolloutArgs&, const RolloutFlags&, cudaStream_t);
+template int launch_lane_rollout_n<SWM_INSTANTIATE_LANE_N>(const RolloutArgs&, const RolloutFlags&, bool, cudaStream_t);
 
 #endif  // SWM_INSTANTIATE_LANE_N
 

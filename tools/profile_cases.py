@@ -31,9 +31,9 @@ def main():
         ac = torch.as_tensor(rng.uniform(-5, 5, (65536, 2))).cuda()
         fn = lambda: S.ops.rollout(p, H, actions=ac, want_final=True)
         B = 65536
-    elif case in ("n5_v2", "n5_v2_thread", "n5_v2_256", "n10_grp"):
-        n, D, R = (10, 512, 128) if case == "n10_grp" else (5, 128 if case == "n5_v2_256" else 1024, 1)
-        kern = S.KERNEL_THREAD if case == "n5_v2_thread" else S.KERNEL_AUTO
+    elif case in ("n5_v2", "n5_v2_thread", "n5_v2_256", "n5_v2_1024", "n10_grp"):
+        n, D, R = (10, 512, 128) if case == "n10_grp" else (5, {"n5_v2_256": 128, "n5_v2_1024": 512}.get(case, 1024), 1)
+        kern = S.KERNEL_THREAD if case == "n5_v2_thread" else int(os.environ.get("SWM_PROFILE_KERNEL", S.KERNEL_AUTO))
         p = S.make_params(n=n)
         no, ws = 2 * n + 2, (n - 1) * (2 * n + 2)
         W = torch.as_tensor(rng.uniform(-1, 1, ws) * 0.05).cuda()
