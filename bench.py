@@ -592,9 +592,15 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
         barrier()
         return out
 
-    def describe(eng, kernel_cfg):
+    KERNEL_TEXT = {"thread": "one thread per environment", "lanes": "lane-split: one environment over %d lanes, one warp per lane group",
+                   "lanes2": "lane-split over %d lanes, two warps per lane group (main + operator warp)"}
+
+    def describe(eng, note=""):
+        name = S.ops.rollout_kernel_choice(eng.params, eng.B_local, rollouts_per_policy=eng.R)
+        lanes = 32 // S.ops.lane_split_envs_per_warp(eng.params.n)
+        text = KERNEL_TEXT[name] % lanes if "%d" in KERNEL_TEXT[name] else KERNEL_TEXT[name]
         return {"launch": "CUDA graph replay" if eng._graph is not None else "eager",
-                "exchange": eng.exchange.transport, "rollout_kernel": kernel_cfg}
+                "exchange": eng.exchange.transport, "rollout_kernel": text + note, "envs_per_gpu": eng.B_local}
 
     # ---------------- config[2]: ARS V2, n = 5, 1,024 directions ----------------
     if 1024 % world == 0:
@@ -613,11 +619,11 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
                      "directions sharded over %d GPU(s) (strong scaling)" % world,
             iters_per_s=K / t, ms_per_iter=1e3 * t / K, env_steps_per_s=K * steps / t, iters_timed=K,
             mean_return_last=float(eng.returns.mean().cpu()), exchange_epochs=ee, parity_vs_single=par,
-            roofline={"bound": "latency (2,048 envs: one lane-split warp per SM sub-partition)",
+            roofline={"bound": "latency (2,048 envs in all: at most one lane-split warp per SM sub-partition)",
                       "executed": {"flops_per_env_step": EXEC_FLOPS["n5_v2"],
                                    "frac": (K * steps / t / world) * EXEC_FLOPS["n5_v2"] / 1e12 / fp64_peak_tflops},
                       "algorithmic_frac": (K * steps / t / world) * W_REF_V2[5] / 1e12 / fp64_peak_tflops},
-            **describe(eng, "lane-split (8 lanes per environment)"))
+            **describe(eng))
         eng.exchange.close()
         del eng
 
@@ -678,7 +684,7 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
             roofline={"bound": "latency (512 + <=512 envs)",
                       "executed": {"flops_per_env_step": EXEC_FLOPS["n3_v1"],
                                    "frac": (K * steps / t / world) * EXEC_FLOPS["n3_v1"] / 1e12 / fp64_peak_tflops}},
-            **describe(eng, "lane-split (4 lanes per environment)"))
+            **describe(eng))
         eng.exchange.close()
         del eng
 
@@ -703,7 +709,7 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
                       "executed": {"flops_per_env_step": EXEC_FLOPS["n10_v2"],
                                    "frac": (K * steps / t / world) * EXEC_FLOPS["n10_v2"] / 1e12 / fp64_peak_tflops},
                       "algorithmic_frac": (K * steps / t / world) * W_REF_V2[10] / 1e12 / fp64_peak_tflops},
-            **describe(eng, "one thread per environment, one policy copy per warp"))
+            **describe(eng, ", one policy copy per warp"))
         eng.exchange.close()
         del eng
 

@@ -244,18 +244,23 @@ int build_rollout_args(const swm_params_t* params, const swm_rollout_t* cfg, Rol
   return SWM_OK;
 }
 
-// AUTO: the lane-split kernel wins while its warps (B * L / 32) still find a sub-partition of their own,
-// or at most share one with a second warp: measured crossover, tools/lane_split_sweep.py.  It is tuned for
-// chains of up to 7 segments (8 lanes per environment).
+// AUTO (measured crossovers, tools/lane_split_sweep.py, profiles/r02_summary.md), for chains of up to 7 segments
+// (8 lanes per environment):
+//   lane groups <= 2 per SM               -> LANES2: main warp + operator warp per group, every warp on a
+//                                            sub-partition of its own (n = 5: 0.30 ms against 0.40 / 0.72 ms)
+//   lane-split warps <= 2 per sub-partition -> LANES (n = 5, 2,048 envs: 0.42 ms against 0.72 ms)
+//   larger batches                        -> THREAD (one environment per thread fills the FP64 units)
 constexpr double kLaneSplitMaxWarpsPerSmsp = 2.0;
+constexpr double kLane2MaxGroupsPerSm = 2.0;
 
 int choose_kernel(int n, const swm_rollout_t* cfg, const RolloutArgs& a, const RolloutFlags& f) {
   const bool ok = lane_split_supported(a, f);
   if (cfg->kernel == SWM_KERNEL_LANES || cfg->kernel == SWM_KERNEL_LANES2) return ok ? cfg->kernel : SWM_ERR_UNSUPPORTED;
   if (cfg->kernel == SWM_KERNEL_THREAD || !ok || n > 7) return SWM_KERNEL_THREAD;
   const int per_warp = 32 / lane_split_lanes(n);
-  const double warps = (double)((cfg->B + per_warp - 1) / per_warp);
-  return warps <= kLaneSplitMaxWarpsPerSmsp * 4.0 * sm_count_cached() ? SWM_KERNEL_LANES : SWM_KERNEL_THREAD;
+  const double groups = (double)((cfg->B + per_warp - 1) / per_warp);
+  if (groups <= kLane2MaxGroupsPerSm * sm_count_cached()) return SWM_KERNEL_LANES2;
+  return groups <= kLaneSplitMaxWarpsPerSmsp * 4.0 * sm_count_cached() ? SWM_KERNEL_LANES : SWM_KERNEL_THREAD;
 }
 
 }  // namespace

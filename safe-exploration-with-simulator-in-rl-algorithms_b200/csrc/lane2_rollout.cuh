@@ -30,6 +30,13 @@
 #pragma once
 #include "lane_rollout.cuh"
 
+#ifndef SWM_LANE2_SS
+#define SWM_LANE2_SS 0   // 1: M publishes (sin^2, sin cos) next to (sin, cos) -- measured 20 % slower; 0: F squares the sines
+#endif
+#ifndef SWM_LANE2_DU4
+#define SWM_LANE2_DU4 0  // four partial sums in M's policy-row dot product (0: two) -- measured equal
+#endif
+
 namespace swm {
 
 constexpr int kLane2Block = 64;
@@ -46,7 +53,7 @@ lane2_rollout_kernel(const RolloutArgs a) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int kRow = 32 * 16;
   // rows of one double2 per lane; + parity where noted
-  enum { ROW_OBS = 0, ROW_T = 1, ROW_R = 2, ROW_PSI = 3, ROW_SC = 4, ROWS = 6 };
+  enum { ROW_OBS = 0, ROW_T = 1, ROW_R = 2, ROW_PSI = 3, ROW_SC = 4, ROW_SS = 6, ROWS = 8 };  // SC, SS: + parity
   // barrier ids: signal base + parity  (0 is __syncthreads)
   enum { BAR_SC = 1, BAR_XT = 3 };
   __shared__ __align__(16) double2 sh[ROWS][32];
@@ -100,14 +107,23 @@ lane2_rollout_kernel(const RolloutArgs a) {
       constexpr int buf = decltype(buf_c)::value;
       named_bar_sync(BAR_SC + buf);                        // (sin, cos)(u) of all segments published by M
       double ss[N], sc[N];
-      double sn = 0.0, cn = 1.0;
+#if SWM_LANE2_SS
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        const double2 v = lds2(gbase, (ROW_SS + buf) * kRow + q * 16);   // (sin^2, sin cos) of segment q
+        ss[q] = v.x;
+        sc[q] = v.y;
+      }
+#else
 #pragma unroll
       for (int q = 0; q < N; ++q) {
         const double2 v = lds2(gbase, (ROW_SC + buf) * kRow + q * 16);
         ss[q] = v.x * v.x;
         sc[q] = v.x * v.y;
-        if (seg == q) { sn = v.x; cn = v.y; }
       }
+#endif
+      const double2 own = lds2(mine, (ROW_SC + buf) * kRow);             // (sin, cos) of this lane's segment
+      const double sn = own.x, cn = own.y;
       // division-free factorisation: E_{j+1} = kappa_{j+1} P_{j+1} - Q_j adj(E_j) Q_j, kappa_{j+1} = det E_j / kappa_j,
       // X_j = (kappa_j / det E_j) adj(E_j), T_{j+1} = Q_j X_j;  P_j = 2I + 3(N_{j-1} + N_j), Q_j = 3 N_j - I
       double V[NV + 1];
@@ -259,6 +275,9 @@ lane2_rollout_kernel(const RolloutArgs a) {
   sincos(th, &s, &c);
   if (a.H > 0) {
     sts2(mine, (ROW_SC + 0) * kRow, make_double2(s, c));
+#if SWM_LANE2_SS
+    sts2(mine, (ROW_SS + 0) * kRow, make_double2(s * s, s * c));
+#endif
     named_bar_arrive(BAR_SC + 0);
   }
 
@@ -303,17 +322,25 @@ lane2_rollout_kernel(const RolloutArgs a) {
     }
     if (t + 1 < a.H) {
       sts2(mine, (ROW_SC + (buf ^ 1)) * kRow, make_double2(sN, cN));
+#if SWM_LANE2_SS
+      sts2(mine, (ROW_SS + (buf ^ 1)) * kRow, make_double2(sN * sN, sN * cN));
+#endif
       named_bar_arrive(BAR_SC + (buf ^ 1));                // angles of step t+1 for F
     }
     double du = du_fixed;
-    if (LINEAR) {
-      double d0 = 0.0, d1 = 0.0;
+    if (LINEAR) {  // four partial sums: the dot product is on the critical path of the step
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
       for (int q = 0; q <= N; ++q) {
-        d0 = fma(D[2 * q], xo[q].x, d0);
-        d1 = fma(D[2 * q + 1], xo[q].y, d1);
+        if (SWM_LANE2_DU4 && (q & 1)) {
+          d2 = fma(D[2 * q], xo[q].x, d2);
+          d3 = fma(D[2 * q + 1], xo[q].y, d3);
+        } else {
+          d0 = fma(D[2 * q], xo[q].x, d0);
+          d1 = fma(D[2 * q + 1], xo[q].y, d1);
+        }
       }
-      du = d0 + d1;
+      du = (d0 + d1) + (d2 + d3);
     }
     double vx = gdx * P.inv_l, vy = gdy * P.inv_l;
 #pragma unroll

@@ -15,7 +15,7 @@ from ._lib import (ARS_AGENT, ARS_RLGLUE, ARS_TOPB, DELTA_01, DELTA_PM1, GYM, PO
 
 __all__ = ["step_batched", "step_batched_models", "accelerations_batched", "rollout", "RolloutResult", "ChunkedRollout", "plan_chunks", "philox_deltas",
            "ars_topb", "ars_update", "pack_exchange", "counter_add", "record_nanmean", "stats_finalize", "stats_merge", "reduce_returns", "screen_mask", "policy_actions", "update_args",
-           "fp64_probe", "obs_dim", "act_dim", "policy_size", "reset_state", "lane_split_envs_per_warp"]
+           "fp64_probe", "obs_dim", "act_dim", "policy_size", "reset_state", "lane_split_envs_per_warp", "rollout_kernel_choice"]
 
 
 def obs_dim(n):
@@ -34,6 +34,18 @@ def lane_split_envs_per_warp(n):
     """Environments per warp (= per stats_partial row) of the lane-split rollout kernel: 32 / L with
     L = 4, 8 or 16 lanes per environment (csrc/lane_rollout.cuh LaneSplit)."""
     return 32 // (4 if n + 1 <= 4 else 8 if n + 1 <= 8 else 16)
+
+
+def rollout_kernel_choice(params, B, *, fixed_actions=False, rollouts_per_policy=1, kernel=0):
+    """Name of the rollout kernel swm_rollout picks for a gym-dynamics batch of B environments on the current
+    device: 'thread' (one thread per environment), 'lanes' (one environment over 4/8/16 lanes) or 'lanes2'
+    (lanes + a second, operator warp per lane group)."""
+    cfg = _lib.SwmRollout()
+    cfg.policy_mode = POLICY_FIXED_ACTION if fixed_actions else POLICY_PHILOX
+    cfg.H, cfg.B, cfg.rollouts_per_policy, cfg.kernel = 1, int(B), int(rollouts_per_policy), int(kernel)
+    k = _lib.lib().swm_rollout_kernel_choice(ctypes.byref(params), ctypes.byref(cfg))
+    _lib.check(min(k, 0))
+    return {_lib.KERNEL_THREAD: "thread", _lib.KERNEL_LANES: "lanes", _lib.KERNEL_LANES2: "lanes2"}[k]
 
 
 def reset_state(n, variant=GYM, device="cuda"):
