@@ -149,3 +149,35 @@ def test_config5_per_gpu_share_grouped_rollouts(S, O):
         assert _close(ret[k, j, r], want), (k, j, r, ret[k, j, r], want)
     red = S.ops.reduce_returns(full, R).cpu().numpy()
     np.testing.assert_allclose(red, ret.reshape(2 * D, R).mean(1), rtol=1e-13)
+
+
+def test_config5_full_million_envs_engine_iteration(S, O):
+    """config[4] at its FULL size on one GPU: 4,096 directions x 2 x 128 rollouts = 1,048,576 ten-segment
+    environments, one ARS V2 engine iteration (graph-free): sampled environments against the oracle, the
+    per-direction means, the count of the V2 statistics, ranking and update against the oracle's update on the
+    engine's own returns."""
+    n, N, R, H, nu, alpha, seed = 10, 4096, 128, 1000, 0.01, 0.0075, 4
+    ps, po = S.make_params(n=n), O.make_params(n=n)
+    no, ws = 2 * n + 2, (n - 1) * (2 * n + 2)
+    rng = np.random.default_rng(6)
+    W0 = rng.uniform(-1, 1, ws) * 0.05
+    eng = S.ArsEngine(ps, N=N, b=N, alpha=alpha, nu=nu, H=H, v2=True, semantics=S.ARS_AGENT, seed=seed,
+                      rollouts_per_direction=R, init_perturb=1e-2, initial_policy=W0, distributed=False)
+    ret = eng.run_iteration(update=False).cpu().numpy().copy()      # [2N] per-direction means
+    per_env = eng.last.returns.cpu().numpy().reshape(N, 2, R)
+    assert per_env.size == 1048576 and np.isfinite(per_env).all()
+    np.testing.assert_allclose(ret, per_env.reshape(2 * N, R).mean(1), rtol=1e-13)
+    start = np.zeros(no)
+    start[2::2] = np.pi / 2
+    for k, j, r in ((0, 0, 0), (N - 1, 1, R - 1), (2047, 0, 64), (1234, 1, 17), (4000, 0, 99)):
+        d = O.philox_delta(seed, 0, k, ws)
+        pert = O.philox_delta(seed, 0, r, no, dist=1, stream=1)
+        want = O.rollout(po, O.GYM, H, policy=W0 + (1, -1)[j] * nu * d, init_state=start + 1e-2 * pert)[0]
+        assert _close(per_env[k, j, r], want), (k, j, r, per_env[k, j, r], want)
+    eng.apply_update()
+    assert float(eng.stats.cpu()[0]) == 2.0 * N * R * H
+    np.testing.assert_array_equal(eng.order.cpu().numpy(), O.sort_directions(ret))
+    deltas = S.ops.philox_deltas(seed, 0, 0, N, ws).cpu().numpy()
+    W1, _ = O.update_policy(W0, deltas, ret, b=N, alpha=alpha, semantics=0)
+    np.testing.assert_allclose(eng.W.cpu().numpy(), W1, rtol=1e-9, atol=1e-12)
+    assert bool(torch.isfinite(eng.inv_sigma).all())
