@@ -165,7 +165,7 @@ typedef struct {
                                    64-step-aligned time chunks on internal streams, joined back into `stream`; needs
                                    final_state as the chaining buffer; results: states bit-identical, returns equal up to
                                    the rounding of the partial sums) from (B, n, SM count) -- see swm_rollout_schedule;
-                                   -1: always one plain launch;  1..16: this many sub-batches (SWM_ERR_UNSUPPORTED if the
+                                   -1: always one plain launch;  1..32: this many sub-batches (SWM_ERR_UNSUPPORTED if the
                                    request cannot be scheduled: trajectory / screening / no final_state / H <= chunk) */
   int32_t schedule_chunk;       /* steps per chunk when schedule_sub > 0: a positive multiple of 64 */
 } swm_rollout_t;

@@ -281,7 +281,7 @@ namespace {
 // pace of the busiest sub-partition.  Cutting the rollout into short launches on several streams (state chained
 // through final_state -> init_state, returns accumulated, chunk boundaries on the exact re-evaluation of the
 // tracked sines/cosines so that every state is bit-identical) lets the hardware re-balance every 64 steps.
-constexpr int kPlanMaxSub = 16;
+constexpr int kPlanMaxSub = 32;
 
 struct Plan {
   int n_sub = 0, chunk = 0;  // n_sub == 0: one plain launch
