@@ -26,10 +26,10 @@ def main():
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     rng = np.random.default_rng(0)
     H = 1000
-    if case == "n3_fixed":
+    if case in ("n3_fixed", "n3_fixed_plain"):   # default call (library schedule) / one forced plain launch
         p = S.make_params(n=3)
         ac = torch.as_tensor(rng.uniform(-5, 5, (65536, 2))).cuda()
-        fn = lambda: S.ops.rollout(p, H, actions=ac, want_final=True)
+        fn = lambda: S.ops.rollout(p, H, actions=ac, want_final=True, schedule="plain" if case.endswith("plain") else None)
         B = 65536
     elif case in ("n5_v2", "n5_v2_thread", "n5_v2_256", "n5_v2_1024", "n10_grp"):
         n, D, R = (10, 512, 128) if case == "n10_grp" else (5, {"n5_v2_256": 128, "n5_v2_1024": 512}.get(case, 1024), 1)
