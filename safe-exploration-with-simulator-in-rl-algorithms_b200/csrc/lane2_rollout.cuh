@@ -30,15 +30,6 @@
 #pragma once
 #include "lane_rollout.cuh"
 
-#ifndef SWM_LANE2_SS
-#define SWM_LANE2_SS 0   // 1: M publishes (sin^2, sin cos) next to (sin, cos) -- measured 20 % slower; 0: F squares the sines
-#endif
-#ifndef SWM_LANE2_FBLOCKS
-#define SWM_LANE2_FBLOCKS 0  // 1: every F lane forms only its own joint's blocks, exchanged inside warp F
-#endif
-#ifndef SWM_LANE2_DU4
-#define SWM_LANE2_DU4 0  // four partial sums in M's policy-row dot product (0: two) -- measured equal
-#endif
 
 namespace swm {
 
@@ -56,7 +47,7 @@ lane2_rollout_kernel(const RolloutArgs a) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int kRow = 32 * 16;
   // rows of one double2 per lane; + parity where noted
-  enum { ROW_OBS = 0, ROW_T = 1, ROW_R = 2, ROW_PSI = 3, ROW_SC = 4, ROW_SS = 6, ROW_P = 8, ROW_Q = 9, ROWS = 10 };  // SC, SS: + parity
+  enum { ROW_OBS = 0, ROW_T = 1, ROW_R = 2, ROW_PSI = 3, ROW_SC = 4, ROWS = 6 };  // SC: + parity
   // barrier ids: signal base + parity  (0 is __syncthreads)
   enum { BAR_SC = 1, BAR_XT = 3 };
   __shared__ __align__(16) double2 sh[ROWS][32];
@@ -112,23 +103,6 @@ lane2_rollout_kernel(const RolloutArgs a) {
       const double2 own = lds2(mine, (ROW_SC + buf) * kRow);             // (sin, cos) of this lane's segment
       const double sn = own.x, cn = own.y;
       double V[NV + 1];
-#if SWM_LANE2_FBLOCKS
-      // this lane forms the blocks of ITS joint (P_i needs the neighbour's sines, which M published too) ...
-      {
-        const double2 prv = lds2(mine, (ROW_SC + buf) * kRow - 16);      // segment seg-1 (lane 0: unused garbage)
-        const double s2 = sn * sn, scn = sn * cn;
-        sts2(mine, ROW_P * kRow, make_double2(fma(3.0, fma(prv.x, prv.x, s2), 2.0), -3.0 * fma(prv.x, prv.y, scn)));
-        sts2(mine, ROW_Q * kRow, make_double2(fma(3.0, s2, -1.0), -3.0 * scn));
-        __syncwarp();
-      }
-      // ... and reads all of them
-      double2 Pb[J > 0 ? J : 1], Qb[J > 1 ? J - 1 : 1];
-#pragma unroll
-      for (int j = 1; j <= J; ++j) Pb[j - 1] = lds2(gbase, ROW_P * kRow + j * 16);
-#pragma unroll
-      for (int j = 1; j < J; ++j) Qb[j - 1] = lds2(gbase, ROW_Q * kRow + j * 16);
-      double ea = Pb[0].x, eb = Pb[0].y, ed = 10.0 - ea;
-#else
       double ss[N], sc[N];
 #pragma unroll
       for (int q = 0; q < N; ++q) {
@@ -139,7 +113,6 @@ lane2_rollout_kernel(const RolloutArgs a) {
       // division-free factorisation: E_{j+1} = kappa_{j+1} P_{j+1} - Q_j adj(E_j) Q_j, kappa_{j+1} = det E_j / kappa_j,
       // X_j = (kappa_j / det E_j) adj(E_j), T_{j+1} = Q_j X_j;  P_j = 2I + 3(N_{j-1} + N_j), Q_j = 3 N_j - I
       double ea = fma(3.0, ss[0] + ss[J > 0 ? 1 : 0], 2.0), eb = -3.0 * (sc[0] + sc[J > 0 ? 1 : 0]), ed = 10.0 - ea;
-#endif
       double kap = 1.0, ikap = 1.0;
 #pragma unroll
       for (int j = 1; j <= J; ++j) {
@@ -149,13 +122,8 @@ lane2_rollout_kernel(const RolloutArgs a) {
         V[3 * (j - 1) + 1] = -rho * eb;
         V[3 * (j - 1) + 2] = rho * ea;
         if (j < J) {
-#if SWM_LANE2_FBLOCKS
-          const double qa = Qb[j - 1].x, qb = Qb[j - 1].y, qd = 1.0 - qa;
-          const double pa = Pb[j].x, pb = Pb[j].y;
-#else
           const double qa = fma(3.0, ss[j], -1.0), qb = -3.0 * sc[j], qd = 1.0 - qa;
           const double pa = fma(3.0, ss[j] + ss[j + 1], 2.0), pb = -3.0 * (sc[j] + sc[j + 1]);
-#endif
           // M = Q adj(E), adj(E) = (ed, -eb; -eb, ea)
           const double m00 = fma(qa, ed, -qb * eb), m01 = fma(qb, ea, -qa * eb);
           const double m10 = fma(qb, ed, -qd * eb), m11 = fma(qd, ea, -qb * eb);
@@ -209,9 +177,6 @@ lane2_rollout_kernel(const RolloutArgs a) {
         }
       }
       named_bar_arrive(BAR_XT + buf);                      // rows y_i(u) ready
-#if SWM_LANE2_FBLOCKS
-      __syncwarp();                                        // the block rows are rewritten by the next call
-#endif
     };
     // one row set per step u = 0 .. H-1 (M publishes the angles of step u+1 during step u, those of step 0
     // before its loop)
@@ -295,9 +260,6 @@ lane2_rollout_kernel(const RolloutArgs a) {
   sincos(th, &s, &c);
   if (a.H > 0) {
     sts2(mine, (ROW_SC + 0) * kRow, make_double2(s, c));
-#if SWM_LANE2_SS
-    sts2(mine, (ROW_SS + 0) * kRow, make_double2(s * s, s * c));
-#endif
     named_bar_arrive(BAR_SC + 0);
   }
 
@@ -342,25 +304,17 @@ lane2_rollout_kernel(const RolloutArgs a) {
     }
     if (t + 1 < a.H) {
       sts2(mine, (ROW_SC + (buf ^ 1)) * kRow, make_double2(sN, cN));
-#if SWM_LANE2_SS
-      sts2(mine, (ROW_SS + (buf ^ 1)) * kRow, make_double2(sN * sN, sN * cN));
-#endif
       named_bar_arrive(BAR_SC + (buf ^ 1));                // angles of step t+1 for F
     }
     double du = du_fixed;
-    if (LINEAR) {  // four partial sums: the dot product is on the critical path of the step
-      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+    if (LINEAR) {
+      double d0 = 0.0, d1 = 0.0;
 #pragma unroll
       for (int q = 0; q <= N; ++q) {
-        if (SWM_LANE2_DU4 && (q & 1)) {
-          d2 = fma(D[2 * q], xo[q].x, d2);
-          d3 = fma(D[2 * q + 1], xo[q].y, d3);
-        } else {
-          d0 = fma(D[2 * q], xo[q].x, d0);
-          d1 = fma(D[2 * q + 1], xo[q].y, d1);
-        }
+        d0 = fma(D[2 * q], xo[q].x, d0);
+        d1 = fma(D[2 * q + 1], xo[q].y, d1);
       }
-      du = (d0 + d1) + (d2 + d3);
+      du = d0 + d1;
     }
     double vx = gdx * P.inv_l, vy = gdy * P.inv_l;
 #pragma unroll

@@ -36,15 +36,6 @@
 
 #include "kernels.cuh"
 
-#ifndef SWM_LANE_VOLATILE_BASE
-#define SWM_LANE_VOLATILE_BASE 0
-#endif
-#ifndef SWM_LANE_UNROLL2
-#define SWM_LANE_UNROLL2 1
-#endif
-#ifndef SWM_LANE_GSEL_FMA
-#define SWM_LANE_GSEL_FMA 0  // e = g_i + g_{i+1} by 0/1-weight FMAs (1) or by predicated adds (0): measured equal
-#endif
 
 namespace swm {
 
@@ -82,12 +73,7 @@ lane_rollout_kernel(const RolloutArgs a) {
 
   const int lane = threadIdx.x;
   const int seg = lane & (L - 1), grp = lane / L;
-#if SWM_LANE_VOLATILE_BASE
-  uint32_t sh_base;  // volatile: computed once here, not rematerialised (S2UR + ULEA) inside the step loop
-  asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(sh_base) : "l"(&sh[0][0]));
-#else
   const uint32_t sh_base = (uint32_t)__cvta_generic_to_shared(&sh[0][0]);
-#endif
   const uint32_t gbase = sh_base + (uint32_t)(grp * L * 16);
   const uint32_t mine = gbase + (uint32_t)(seg * 16);
   const bool is_seg = seg < N;
@@ -181,12 +167,6 @@ lane_rollout_kernel(const RolloutArgs a) {
   double om[N];
 #pragma unroll
   for (int q = 0; q < N; ++q) om[q] = (N - q - 0.5) / N - (q < seg ? 1.0 : 0.0) - (q == seg ? 0.5 : 0.0);
-
-  // e_i = g_i + g_{i+1} (joint forces at the head and the tail of this segment) as a sum over all joints with
-  // per-lane 0/1 weights: J constant-weight FMAs per component instead of 8 J predicated moves
-  double gsel[J > 0 ? J : 1];
-#pragma unroll
-  for (int j = 1; j <= J; ++j) gsel[j - 1] = (seg == j || seg == j - 1) ? 1.0 : 0.0;
 
   bool skipped = false;  // reward-constraint safe exploration: a screened-out direction is not rolled out
   if (LINEAR && a.dir_mask) skipped = a.dir_mask[(e / a.R) >> 1] == 0;
@@ -360,12 +340,7 @@ lane_rollout_kernel(const RolloutArgs a) {
           y = fma(-T3[j - 1], gy, fma(-T1[j - 1], gx, y));
         }
         gx = x; gy = y;
-#if SWM_LANE_GSEL_FMA
-        ex = fma(gsel[j - 1], gx, ex);
-        ey = fma(gsel[j - 1], gy, ey);
-#else
         if (seg == j || seg == j - 1) { ex += gx; ey += gy; }
-#endif
       }
     }
     const double thdd = fma(3.0, fma(c, ey, -s * ex), tau);
@@ -393,7 +368,6 @@ lane_rollout_kernel(const RolloutArgs a) {
     if (traj) *reinterpret_cast<double2*>(traj + (long long)t * traj_step) = make_double2(oa, ob);
     factorise(1, JM, buf ^ 1);  // first half of step t+1's chain, from the blocks published before round 2
   };
-#if SWM_LANE_UNROLL2
   {
     int t = 0;
     for (; t + 1 < a.H; t += 2) {
@@ -402,16 +376,6 @@ lane_rollout_kernel(const RolloutArgs a) {
     }
     if (t < a.H) step(t, std::integral_constant<int, 0>());
   }
-#else
-  {
-    uint32_t gb0 = gbase, mn0 = mine;  // parity of the step folded into the base addresses: buffer 0 is always "this step"
-    (void)gb0; (void)mn0;
-    for (int t = 0; t < a.H; ++t) {
-      if (t & 1) step(t, std::integral_constant<int, 1>());
-      else step(t, std::integral_constant<int, 0>());
-    }
-  }
-#endif
 
   if (live) {
     if (seg == 0) {
