@@ -299,7 +299,7 @@ SWM_API int swm_record_nanmean(const double* x, int n, double* curve, const uint
  *     the data path, so the whole iteration can be captured in a CUDA graph.  Setup (once): every rank
  *     calls swm_exchange_create, exports swm_exchange_ipc_handle (SWM_IPC_HANDLE_BYTES bytes), the host
  *     layer all-gathers the handles (torch.distributed / MPI / files) and passes the table to
- *     swm_exchange_open_peers.  A peer that does not answer within ~2 s sets a sticky status
+ *     swm_exchange_open_peers.  A peer that does not answer within ~10 s sets a sticky status
  *     (swm_exchange_status) instead of hanging the device;
  *   - collective fallback (no peer access): call once with record_out set and gathered_world = world
  *     (pack only), all-gather record_out with the host's collective, then call with gathered_in. */

@@ -12,8 +12,9 @@
 // Synchronisation: flags are monotone epochs (one 64-bit word per source rank, in the DESTINATION's buffer);
 // data slots are double-buffered by epoch parity, so a fast rank can never overwrite a record that a slow
 // rank is still reading: writing epoch e+2 needs the slow rank's flag e+1, which it only publishes after its
-// stream finished consuming epoch e.  A wait that exceeds ~2 s sets a sticky status word and falls
-// through (the launch returns, the host sees swm_exchange_status != 0) instead of hanging the GPU.
+// stream finished consuming epoch e.  A wait that exceeds ~10 s sets a sticky status word and falls
+// through (the launch returns, the host sees swm_exchange_status != 0; later exchanges no longer wait)
+// instead of hanging the GPU.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -26,7 +27,7 @@ namespace swm {
 
 constexpr int kExBlock = 1024;
 constexpr int kMaxWorld = 16;
-constexpr long long kWaitCycles = 4000000000LL;  // ~2 s at 1.9 GHz
+constexpr long long kWaitCycles = 20000000000LL;  // ~10 s at 1.9 GHz
 
 struct ExchangeDev {
   unsigned long long epoch;    // exchanges completed by this rank
@@ -149,8 +150,9 @@ __global__ void __launch_bounds__(kExBlock) pack_exchange_kernel(const PackArgs 
       const unsigned long long* flag =
           reinterpret_cast<const unsigned long long*>(a.local + 2ull * a.world * a.slot_bytes) + tid;
       const long long t0 = clock64();
+      const bool dead = dev->status != 0ull;  // a peer already timed out once: do not wait for it again
       while (ld_acquire_sys(flag) < epoch) {
-        if (clock64() - t0 > kWaitCycles) {
+        if (dead || clock64() - t0 > kWaitCycles) {
           atomicCAS(&dev->status, 0ull, 1ull + (unsigned long long)tid);
           break;
         }

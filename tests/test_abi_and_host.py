@@ -182,3 +182,25 @@ def test_chunk_plan_partition(S):
         S.ops.plan_chunks(128, 1, 4, 1000, 100)   # not a multiple of 64
     with pytest.raises(ValueError):
         S.ops.plan_chunks(130, 4, 4, 1000, 64)    # would split a direction
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_shared_config():
+    """`bench.py --impl reference` (the CPU arm the driver launches next to the GPU arm): exactly one JSON line
+    on stdout, the contract keys, and a `config` dict identical to the GPU arm's (bench.CONFIG)."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--no-cpu"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                         timeout=300)
+    assert out.returncode == 0
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["impl"] == "reference" and line["config"] == bench.CONFIG and line["metric"] == bench.METRIC
+    for key in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+                "data", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["value"] > 1e5 and line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
