@@ -56,8 +56,8 @@ Phys make_phys(const swm_params_t* p) {
   P.kappa = k * l / m;
   P.m2kappa = -2.0 * (k * l / m);
   P.u_scale = 12.0 / (m * l * l);
-  P.gdd_c = l / (2.0 * n);
-  P.h_gdd_c = p->h * (l / (2.0 * n));
+  P.gdd_c = P.m2kappa * (l / (2.0 * n));
+  P.h_gdd_c = p->h * P.gdd_c;
   P.inv_n = 1.0 / n;
   P.kl = k * l;
   P.tau_c = k * (l * l * l) / 12.0;

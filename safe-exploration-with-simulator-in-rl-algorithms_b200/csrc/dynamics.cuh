@@ -31,10 +31,10 @@ struct Phys {
   // gym variant, non-dimensional form (lengths in units of l, forces in units of m*l/2)
   double inv_l;      // 1/l
   double kappa;      // k*l/m       (friction torque coefficient: tau_i/I = kappa*thd_i + ...)
-  double m2kappa;    // -2*k*l/m    (psi_i = m2kappa * (v_i.n_i) * n_i)
+  double m2kappa;    // -2*k*l/m    (psi_i = F_i n_i, F_i = m2kappa * (v_i.n_i))
   double u_scale;    // 12/(m*l^2)  (torques enter as u/I)
-  double gdd_c;      // l/(2n)      (Gdd = gdd_c * sum_i psi_i)
-  double h_gdd_c;    // h*l/(2n)    (Euler update of Gdot straight from sum_i psi_i)
+  double gdd_c;      // m2kappa*l/(2n)    (Gdd = gdd_c * sum_i (v_i.n_i) n_i: the friction coefficient is folded in)
+  double h_gdd_c;    // h*m2kappa*l/(2n)  (Euler update of Gdot straight from sum_i (v_i.n_i) n_i)
   double inv_n;      // 1/n
   // rlglue variant
   double kl;         // k*l
@@ -86,7 +86,9 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
                                                   const double (&thd)[N], const double* ut,
                                                   double& psx, double& psy, double (&thdd)[N],
                                                   double* fs = nullptr) {
-  // Outputs: thdd, and (psx, psy) = sum_i psi_i; the caller scales it (Gdd = gdd_c * sum).
+  // Outputs: thdd, and (psx, psy) = sum_i (v_i.n_i) n_i = sum_i psi_i / m2kappa; the caller scales it
+  // (Gdd = gdd_c * sum, gdd_c carries m2kappa), so the friction force itself is never formed: it enters the
+  // right-hand sides as F -+ tau~ = fma(m2kappa, v.n, -+tau~), one operation less per segment.
   // Streaming formulation: apart from the factorisation (5 doubles per joint) everything is a
   // rolling value, so the live state is O(N) with a small constant (registers, no local memory).
   //
@@ -118,7 +120,7 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
   double rx[JR], ry[JR];          // eliminated right-hand sides
   double pXa = 0.0, pXb = 0.0, pXd = 0.0, prx = 0.0, pry = 0.0;  // FS > 0: the previous joint's values (registers)
   double ax = sx, ay = sy;          // velocity of the joint at the head of segment i
-  double sumx = 0.0, sumy = 0.0;    // sum_i F_i n_i
+  double sumx = 0.0, sumy = 0.0;    // sum_i (v_i.n_i) n_i
   double Bpx = 0.0, Bpy = 0.0;      // B_{i-1}
   double ssp = 0.0, scp = 0.0;      // s^2, s c of segment i-1
 #pragma unroll
@@ -126,9 +128,9 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
     const double ts = KEEP ? tsa[i] : opaque(thd[i]) * s[i], tc = KEEP ? tca[i] : opaque(thd[i]) * c[i];
     const double vx = fma(-0.5, ts, ax), vy = fma(0.5, tc, ay);
     if (i + 1 < N) { ax -= ts; ay += tc; }
-    const double F = P.m2kappa * fma(vy, c[i], -vx * s[i]);
-    sumx = fma(-F, s[i], sumx);
-    sumy = fma(F, c[i], sumy);
+    const double vn = fma(vy, c[i], -vx * s[i]);  // F_i = m2kappa * vn
+    sumx = fma(-vn, s[i], sumx);
+    sumy = fma(vn, c[i], sumy);
     double du = 0.0;
     if (i >= 1 && i <= N - 2) du = ut[i - 1] - ut[i];
     else if (i >= 1) du = ut[i - 1];
@@ -138,7 +140,7 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
     const double ss = s[i] * s[i], sc = s[i] * c[i];
     if (i >= 1) {
       // A_i = psi_i - w^_i = (F - tau~) n_i + thd^2 p_i
-      const double a = F - tau;
+      const double a = fma(P.m2kappa, vn, -tau);
       const double Ax = fma(-a, s[i], thd[i] * tc), Ay = fma(a, c[i], thd[i] * ts);
       // joint j = i: P_j = 2I + 3(N_{i-1} + N_i); cc = 1 - ss  =>  pd = 10 - pa, qd = 1 - qa
       double pa = fma(3.0, ssp + ss, 2.0);
@@ -180,7 +182,7 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
     }
     if (i <= N - 2) {
       // B_i = psi_i + w^_i = (F + tau~) n_i - thd^2 p_i
-      const double b = F + tau;
+      const double b = fma(P.m2kappa, vn, tau);
       Bpx = -fma(b, s[i], thd[i] * tc);
       Bpy = fma(b, c[i], -thd[i] * ts);
     }
@@ -206,6 +208,7 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
       y0 = rx[FS ? 0 : j - 1]; y1 = ry[FS ? 0 : j - 1];
     }
     if (j < J) {
+      // same expressions as pass 1: the compiler keeps or rebuilds them as register pressure allows
       const double qa = fma(3.0, s[j] * s[j], -1.0), qb = -3.0 * (s[j] * c[j]), qd = 1.0 - qa;
       y0 = fma(-qb, gny, fma(-qa, gnx, y0));
       y1 = fma(-qd, gny, fma(-qb, gnx, y1));
@@ -227,8 +230,8 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
 //   base, |d| <= 1/32: sin to d^5, cos to d^6     truncation <= 5.8e-15 at the limit and ~(32 d)^7 of
 //                                                 that below it (1e-19 at |thd| = 7 rad/s, h = 1e-3)
 //   tail, |d| <= 1/8 : + the d^7, d^9 terms of sin and the d^8, d^10 terms of cos (truncation < 3e-17)
-// The tail is added under a per-lane branch: a warp whose lanes are all slow skips it, a mixed warp
-// pays 8 more operations per segment, and no lane's result depends on its neighbours.  The rollout
+// The tail is added under a per-lane, per-segment branch: a warp skips it for a segment that is slow in all
+// its lanes, pays 8 more operations for one that is not, and no lane's result depends on its neighbours.  The rollout
 // kernel re-evaluates (s, c) exactly from th every 64th step, so truncation never accumulates over
 // more than 63 steps.
 constexpr double kRotateShort = 0.03125, kRotateLong = 0.125;
@@ -528,11 +531,12 @@ __device__ __forceinline__ void gym_step_tracked(const Phys& P, double& gdx, dou
   // max_i |d_i| is taken as the maximum of the sign-stripped high words (NaN / Inf have the largest ones
   // and fall through to sincos).  Thresholds are powers of two (low word 0): hi <= hi(threshold) admits
   // |d| < threshold * (1 + 2^-20), which the polynomial bounds cover.
-  int dmax_hi = 0;
+  int dmax_hi = 0, d_hi[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     d[i] = P.h * thd[i];
-    dmax_hi = max(dmax_hi, __double2hiint(d[i]) & 0x7fffffff);
+    d_hi[i] = __double2hiint(d[i]) & 0x7fffffff;
+    dmax_hi = max(dmax_hi, d_hi[i]);
     th[i] = fma(P.h, thd[i], th[i]);
     thd[i] = fma(P.h, thdd[i], thd[i]);
   }
@@ -550,10 +554,11 @@ __device__ __forceinline__ void gym_step_tracked(const Phys& P, double& gdx, dou
   for (int i = 0; i < N; ++i) rotate_by(sn[i], cm1[i], s[i], c[i]);
   return;
 #endif
-  if (dmax_hi > kRotateShortHi) {
+  // the tail per segment (as the lane-split kernels decide it): with one branch for all segments of a lane a
+  // warp pays 8N operations as soon as any of its 32N increments exceeds 1/32
 #pragma unroll
-    for (int i = 0; i < N; ++i) small_sincos_tail(d[i], z[i], sn[i], cm1[i]);
-  }
+  for (int i = 0; i < N; ++i)
+    if (d_hi[i] > kRotateShortHi) small_sincos_tail(d[i], z[i], sn[i], cm1[i]);
   if (resync || dmax_hi > kRotateLongHi) {
 #pragma unroll
     for (int i = 0; i < N; ++i) sincos(th[i], &s[i], &c[i]);

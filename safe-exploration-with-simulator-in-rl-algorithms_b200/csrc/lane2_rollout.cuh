@@ -322,15 +322,15 @@ lane2_rollout_kernel(const RolloutArgs a) {
       vx = fma(om[q], tq[q].x, vx);
       vy = fma(-om[q], tq[q].y, vy);
     }
-    const double F = P.m2kappa * fma(vy, c, -vx * s);
+    const double vn = fma(vy, c, -vx * s);  // F = m2kappa * vn; h_gdd_c carries m2kappa for the sum below
     const double tau = fma(P.kappa, thd, du);
     const double ttc = thd * tc, tts = thd * ts;
-    const double am = F - tau, bp = F + tau;
+    const double am = fma(P.m2kappa, vn, -tau), bp = fma(P.m2kappa, vn, tau);
     const double Ax = fma(-am, s, ttc), Ay = fma(am, c, tts);
     const double Bx = -fma(bp, s, ttc), By = fma(bp, c, -tts);
     const double Bpx = __shfl_up_sync(FULL, Bx, 1, L), Bpy = __shfl_up_sync(FULL, By, 1, L);
     // ---- round 2 ----
-    sts2(mine, ROW_PSI * kRow, is_seg ? make_double2(-F * s, F * c) : make_double2(0.0, 0.0));
+    sts2(mine, ROW_PSI * kRow, is_seg ? make_double2(-vn * s, vn * c) : make_double2(0.0, 0.0));
     sts2(mine, ROW_R * kRow, make_double2(Ax - Bpx, Ay - Bpy));
     __syncwarp();
     // thdd_i = tau_i + y_i . r  (the block-tridiagonal solve was folded into y_i by warp F, which forms the rows
