@@ -230,8 +230,8 @@ __device__ __forceinline__ void gym_accelerations(const Phys& P, const double (&
 //   base, |d| <= 1/32: sin to d^5, cos to d^6     truncation <= 5.8e-15 at the limit and ~(32 d)^7 of
 //                                                 that below it (1e-19 at |thd| = 7 rad/s, h = 1e-3)
 //   tail, |d| <= 1/8 : + the d^7, d^9 terms of sin and the d^8, d^10 terms of cos (truncation < 3e-17)
-// The tail is added under a per-lane, per-segment branch: a warp skips it for a segment that is slow in all
-// its lanes, pays 8 more operations for one that is not, and no lane's result depends on its neighbours.  The rollout
+// The tail is added under a per-lane branch: a warp whose lanes are all slow skips it, a mixed warp
+// pays 8 more operations per segment, and no lane's result depends on its neighbours.  The rollout
 // kernel re-evaluates (s, c) exactly from th every 64th step, so truncation never accumulates over
 // more than 63 steps.
 constexpr double kRotateShort = 0.03125, kRotateLong = 0.125;
@@ -531,12 +531,11 @@ __device__ __forceinline__ void gym_step_tracked(const Phys& P, double& gdx, dou
   // max_i |d_i| is taken as the maximum of the sign-stripped high words (NaN / Inf have the largest ones
   // and fall through to sincos).  Thresholds are powers of two (low word 0): hi <= hi(threshold) admits
   // |d| < threshold * (1 + 2^-20), which the polynomial bounds cover.
-  int dmax_hi = 0, d_hi[N];
+  int dmax_hi = 0;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     d[i] = P.h * thd[i];
-    d_hi[i] = __double2hiint(d[i]) & 0x7fffffff;
-    dmax_hi = max(dmax_hi, d_hi[i]);
+    dmax_hi = max(dmax_hi, __double2hiint(d[i]) & 0x7fffffff);
     th[i] = fma(P.h, thd[i], th[i]);
     thd[i] = fma(P.h, thdd[i], thd[i]);
   }
@@ -554,11 +553,13 @@ __device__ __forceinline__ void gym_step_tracked(const Phys& P, double& gdx, dou
   for (int i = 0; i < N; ++i) rotate_by(sn[i], cm1[i], s[i], c[i]);
   return;
 #endif
-  // the tail per segment (as the lane-split kernels decide it): with one branch for all segments of a lane a
-  // warp pays 8N operations as soon as any of its 32N increments exceeds 1/32
+  // One branch for all segments of a lane.  (A branch per segment would skip the tail for segments that are
+  // slow in every lane, ~7 FP64 operations per step fewer for n = 3 -- measured 1.7 % SLOWER there and 18 %
+  // slower for n = 10: N divergent regions per step cost more than they save, profiles/r02_summary.md.)
+  if (dmax_hi > kRotateShortHi) {
 #pragma unroll
-  for (int i = 0; i < N; ++i)
-    if (d_hi[i] > kRotateShortHi) small_sincos_tail(d[i], z[i], sn[i], cm1[i]);
+    for (int i = 0; i < N; ++i) small_sincos_tail(d[i], z[i], sn[i], cm1[i]);
+  }
   if (resync || dmax_hi > kRotateLongHi) {
 #pragma unroll
     for (int i = 0; i < N; ++i) sincos(th[i], &s[i], &c[i]);
