@@ -1,6 +1,7 @@
 """Small invocations of every kernel family (all policy-storage modes, V2 moments in registers and in
-shared memory, screening, trajectories, ragged last block, ARS epilogue) for
-`compute-sanitizer --tool memcheck python tools/sanitize_cases.py`."""
+shared memory, screening, trajectories, ragged last block, ARS epilogue, every rollout kernel: per-thread,
+lane-split, lane-split with operator warp; the RL-Glue protocol kernel) for
+`compute-sanitizer --tool memcheck|racecheck|synccheck python tools/sanitize_cases.py [n ...]`."""
 import os
 import sys
 
@@ -36,6 +37,15 @@ def main(ns=(2, 3, 4, 5, 6, 7, 8, 9, 10)):
             S.ops.rollout(p, H, B=Bp, base_policy=W, nu=0.05, seed=3, rollouts_per_policy=R, want_final=True)
             S.ops.rollout(p, H, B=Bp, variant=S.RLGLUE, base_policy=W, nu=0.05, seed=3, rollouts_per_policy=R,
                           clip_actions=True, delta_dist=S.DELTA_01)
+        # the three rollout kernels forced (AUTO picks by batch size): fixed actions, V1, V2 + moments, trajectories
+        for kern in (S._lib.KERNEL_THREAD, S._lib.KERNEL_LANES, S._lib.KERNEL_LANES2):
+            S.ops.rollout(p, H, actions=ac, want_final=True, want_trajectory=True, kernel=kern)
+            S.ops.rollout(p, H, B=2 * 9, base_policy=W, nu=0.05, seed=3, want_final=True, kernel=kern)
+            r = S.ops.rollout(p, H, B=2 * 5 * 3, base_policy=W, nu=0.05, seed=3, rollouts_per_policy=3, init_perturb=1e-2,
+                              mean=mean, inv_sigma=inv, stats_pivot=piv, kernel=kern, schedule="plain")
+            assert bool(torch.isfinite(r.returns).all())
+        ex = S.RlglueArsExperiment(n_seg=n, N=2, b=1, H=9, protocol="reference", replicas=3)
+        assert np.isfinite(ex.run_training(2)).all()
         sim = S.make_params(n=n, l_i=1.01, m_i=0.99, k=10.1)
         S.ops.rollout(p, H, B=70, base_policy=W, nu=0.05, seed=3,
                       screen=dict(sim_params=sim, sim_thresh=0.5, real_thresh=0.6), want_trajectory=True)
@@ -49,4 +59,4 @@ def main(ns=(2, 3, 4, 5, 6, 7, 8, 9, 10)):
 
 
 if __name__ == "__main__":
-    main()
+    main(tuple(int(a) for a in sys.argv[1:]) or (2, 3, 4, 5, 6, 7, 8, 9, 10))
