@@ -347,6 +347,8 @@ lane2_rollout_kernel(const RolloutArgs a) {
       acc1 = fma(yrow[j - 1].y, rj.y, acc1);
     }
     const double thdd = acc0 + acc1;
+    // (the shuffle butterfly of lane_rollout.cuh instead of this row: 6-12 % slower here for n = 3 and 5, M's
+    // step is a latency chain and the row read hides behind the barrier wait; profiles/r02_summary.md)
     double psx = 0.0, psy = 0.0;
 #pragma unroll
     for (int q = 0; q < N; ++q) {

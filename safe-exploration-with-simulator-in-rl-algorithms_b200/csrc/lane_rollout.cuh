@@ -58,6 +58,15 @@ __device__ __forceinline__ double2 lds2(uint32_t addr, int off) {
   return v;
 }
 
+// Sum of v over the L lanes of an environment by xor butterfly.  Both partners of a level add the same two
+// values, so every lane ends with the bitwise identical sum (Gdot is replicated per lane and must stay so).
+template <int L>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int off = 1; off < L; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
 template <int N, bool LINEAR, bool NORM, bool STATS>
 __global__ void __launch_bounds__(kLaneBlock)
 lane_rollout_kernel(const RolloutArgs a) {
@@ -68,8 +77,8 @@ lane_rollout_kernel(const RolloutArgs a) {
   // friction force, and two buffers (step parity) of the joint blocks P and Q.  Addressed through 32-bit
   // shared-window addresses computed once: row r of this lane's environment starts at gbase + r * kRow.
   constexpr int kRow = 32 * 16;
-  enum { ROW_OBS = 0, ROW_T = 1, ROW_R = 2, ROW_PSI = 3, ROW_P = 4, ROW_Q = 6 };  // P, Q: + parity
-  __shared__ __align__(16) double2 sh[8][32];
+  enum { ROW_OBS = 0, ROW_T = 1, ROW_R = 2, ROW_P = 3, ROW_Q = 5 };  // P, Q: + parity
+  __shared__ __align__(16) double2 sh[7][32];
 
   const int lane = threadIdx.x;
   const int seg = lane & (L - 1), grp = lane / L;
@@ -306,9 +315,12 @@ lane_rollout_kernel(const RolloutArgs a) {
     const double Ax = fma(-am, s, ttc), Ay = fma(am, c, tts);
     const double Bx = -fma(bp, s, ttc), By = fma(bp, c, -tts);
     const double Bpx = __shfl_up_sync(FULL, Bx, 1, L), Bpy = __shfl_up_sync(FULL, By, 1, L);
+    // sum_q (v_q.n_q) n_q over the environment's lanes: log2(L) shuffle levels instead of a shared-memory row
+    // read back by every lane (N additions per component and N + 1 wavefronts of the SM-wide shared-memory
+    // pipe); independent of round 2, it overlaps the exchange below
+    const double psx = group_sum<L>(is_seg ? -vn * s : 0.0), psy = group_sum<L>(is_seg ? vn * c : 0.0);
 
     // ---- round 2 ----
-    sts2(mine, ROW_PSI * kRow, is_seg ? make_double2(-vn * s, vn * c) : make_double2(0.0, 0.0));
     sts2(mine, ROW_R * kRow, make_double2(Ax - Bpx, Ay - Bpy));  // r_i, meaningful for joints 1..J
     __syncwarp();
     // right-hand sides with this step's factorisation: r'_j = r_j - T_j r'_{j-1}, w_j = X_j r'_j
@@ -340,17 +352,12 @@ lane_rollout_kernel(const RolloutArgs a) {
           y = fma(-T3[j - 1], gy, fma(-T1[j - 1], gx, y));
         }
         gx = x; gy = y;
+        // (picking g_seg, g_{seg+1} with selects instead of 2J predicated additions: 6 FP64 instructions fewer
+        // for n = 5, measured slower for n = 3 and 7, profiles/r02_summary.md)
         if (seg == j || seg == j - 1) { ex += gx; ey += gy; }
       }
     }
     const double thdd = fma(3.0, fma(c, ey, -s * ex), tau);
-    double psx = 0.0, psy = 0.0;
-#pragma unroll
-    for (int q = 0; q < N; ++q) {
-      const double2 pq = lds2(gbase, ROW_PSI * kRow + q * 16);
-      psx += pq.x;
-      psy += pq.y;
-    }
     // ---- explicit Euler (remy_swimmer_env.py:88-91), reward = Gdot_new . direction ----
     gdx = fma(P.h_gdd_c, psx, gdx);
     gdy = fma(P.h_gdd_c, psy, gdy);
