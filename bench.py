@@ -649,39 +649,54 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
         alpha_h = S.Threshold(K=1., A=0.1, B=0.001).compute_alpha(1000)
         del pre, probe
 
-        def make3(sharded):
+        def make3(sharded, speculate=True):
             return S.ArsEngine(real, seed=12, sim_params=sim, sim_threshold=thr, initial_policy=W0, use_graph=True,
-                               distributed=None if sharded else False, **base)
+                               distributed=None if sharded else False, speculate=speculate, **base)
+
+        def run3(eng, K):
+            for _ in range(5):
+                eng.run_iteration()
+            barrier()
+            pass0 = int(eng.n_pass_total.cpu()[0])  # device-side running count of surviving directions (this rank)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(K):
+                eng.run_iteration()
+            e1.record(stream)
+            barrier()
+            t = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
+            npass = torch.tensor([float(int(eng.n_pass_total.cpu()[0]) - pass0)], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(npass)
+            return t, float(npass.cpu()[0]) / (K * 256.0), eng.check_exchange()
+
         par = parity(make3)
-        eng = make3(True)
         K = 20
-        for _ in range(5):
-            eng.run_iteration()
-        barrier()
-        pass0 = int(eng.n_pass_total.cpu()[0])      # device-side running count of surviving directions (this rank)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(K):
-            eng.run_iteration()
-        e1.record(stream)
-        barrier()
-        t = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
-        npass = torch.tensor([float(int(eng.n_pass_total.cpu()[0]) - pass0)], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(npass)
-        frac_pass = float(npass.cpu()[0]) / (K * 256.0)
+        # the same iterations with the real-world rollouts started only after the screening mask exists
+        eng = make3(True, speculate=False)
+        t_first, frac_first, _ = run3(eng, K)
+        eng.exchange.close()
+        del eng
+        eng = make3(True)
+        t, frac_pass, ee = run3(eng, K)
         steps = (2.0 * 256 + 2.0 * 256 * frac_pass) * 1000
-        ee = eng.check_exchange()
         res["config[3]"] = dict(
             workload="config[3]: safe-exploration ARS V1 (reward constraint), 3-segment swimmer, 256 directions: 512 simulator "
                      "rollouts screen every +-delta pair, surviving pairs are rolled out in the real world; real (l,m,k) = "
                      "(0.8,1.2,10.2), simulator = real + 1e-3 u/|u|, pre-trained W0; sharded over %d GPU(s)" % world,
             iters_per_s=K / t, ms_per_iter=1e3 * t / K, env_steps_per_s=K * steps / t, iters_timed=K,
             screened_fraction=1.0 - frac_pass, sim_threshold=thr,
+            schedule="speculative (engine default for V1 safe mode): the real-world rollouts of all 256 directions run beside "
+                     "the simulator rollouts on a second stream, the screening mask is applied to their returns afterwards; "
+                     "bit-identical to screening first (tests/test_parity_ars.py); env_steps_per_s counts the simulator "
+                     "rollouts and the SURVIVING real rollouts only",
+            screen_first={"iters_per_s": K / t_first, "ms_per_iter": 1e3 * t_first / K, "screened_fraction": 1.0 - frac_first,
+                          "note": "speculate=False: simulator rollouts, mask, then the surviving real rollouts (two dependent "
+                                  "1000-step rollouts per iteration)"},
             threshold_note="threshold = median of min(r+_sim, r-_sim) of a probe iteration; the reference adds "
                            "alpha(H) * eps = %.3g to its threshold (ars_agent.py:64-69), constant, already inside" % (alpha_h * eps),
             exchange_epochs=ee, parity_vs_single=par,
-            roofline={"bound": "latency (512 + <=512 envs)",
+            roofline={"bound": "latency (512 + 512 envs side by side)",
                       "executed": {"flops_per_env_step": EXEC_FLOPS["n3_v1"],
                                    "frac": (K * steps / t / world) * EXEC_FLOPS["n3_v1"] / 1e12 / fp64_peak_tflops}},
             **describe(eng))

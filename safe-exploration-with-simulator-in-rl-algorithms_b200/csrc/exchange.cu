@@ -97,7 +97,11 @@ __global__ void __launch_bounds__(kExBlock) pack_exchange_kernel(const PackArgs 
   for (int g = tid; g < n2; g += kExBlock) {
     double acc = 0.0;
     for (int r = 0; r < a.R; ++r) acc += a.returns_local[(long long)g * a.R + r];
-    rec[g] = a.R > 1 ? acc / a.R : acc;
+    acc = a.R > 1 ? acc / a.R : acc;
+    // a screened-out direction has no real-world return, whether its rollouts were skipped (the rollout kernel
+    // already wrote NaN) or ran speculatively beside the simulator rollouts that screen them (engine.py)
+    if (a.mask_local && a.mask_local[g >> 1] == 0) acc = __longlong_as_double(0x7ff8000000000000LL);
+    rec[g] = acc;
   }
   if (a.mask_local)
     for (int k = tid; k < a.n_local; k += kExBlock) rec[moff + k] = a.mask_local[k] != 0 ? 1.0 : 0.0;

@@ -4,6 +4,8 @@ ARSAgent.runOneIteration (ars/ars_agent.py:132-185) and Basic_ARS.train (safe_ar
 One iteration =
   1. [reward-constraint safe mode] 2N simulator rollouts -> screening mask        (swm_rollout, swm_screen_mask)
   2. 2N (x R) real rollouts, all in one fused kernel launch                        (swm_rollout)
+     (V1 safe mode: 1 and 2 run side by side on two streams, the mask is applied to the returns in step 3 --
+     `speculate`; otherwise 2 rolls out the survivors of 1 only)
   3. ONE launch that packs this rank's record (per-direction mean returns, screening mask, V2 moment
      record), exchanges it with every other rank over NVLink peer memory and unpacks all ranks'
      records                                                                       (swm_ars_pack_exchange)
@@ -34,7 +36,7 @@ class ArsEngine:
                  clip_actions=False, init_perturb=0.0, initial_policy=None, group=None,
                  distributed=None, device=None, sim_params=None, sim_threshold=None,
                  step_screen=None, use_graph=False, curve_capacity=0, rollout_chunks=None, transport="auto",
-                 rollout_kernel=0):
+                 rollout_kernel=0, speculate=True):
         _lib.require_cuda()
         self.params, self.N, self.b, self.alpha, self.nu, self.H = params, int(N), int(b), alpha, nu, int(H)
         self.v2, self.semantics, self.R = bool(v2), semantics, int(rollouts_per_direction)
@@ -72,6 +74,13 @@ class ArsEngine:
         self.pivot = ops.reset_state(n, variant, self.device)
         # reward-constraint screening through a simulator model (ars_agent.py:144-157)
         self.sim_params, self.sim_threshold = sim_params, sim_threshold
+        # speculate: the real-world rollouts of ALL directions run beside the simulator rollouts that screen them
+        # (second stream; both are small batches that leave most of the chip idle) and the screening mask is
+        # applied to their returns afterwards (swm_ars_pack_exchange writes NaN for screened-out directions).
+        # Results are bit-identical to screening first: a rollout never depends on the mask.  Only where nothing
+        # else of a screened-out rollout is kept: not with V2 statistics, not when trajectories are requested.
+        self.speculate = bool(speculate) and sim_params is not None and not self.v2
+        self._side = torch.cuda.Stream(device=self.device) if self.speculate else None
         # per-step state-constraint screening (safe_ars/ars.py:124-153)
         self.step_screen = step_screen
         # persistent buffers: the iteration loop allocates nothing
@@ -152,14 +161,26 @@ class ArsEngine:
         Nl, R = self.N_local, self.R
         deltas_local = None if deltas is None else deltas.reshape(self.N, self.ws)[self.dir0:self.dir0 + Nl]
         dir_mask = None
-        if self.sim_params is not None:
+        def screen():
             sim = self._rollouts(self.sim_params, self._sim_out, deltas_local, None, False, False, None)
             sim_ret = sim.returns if R == 1 else ops.reduce_returns(sim.returns, R, out=self.sim_returns)
             self.sim_returns = sim_ret
             ops.screen_mask(sim_ret, self.sim_threshold, self.mask_local, self.n_pass_local, self.n_pass_total)
+
+        if self.sim_params is not None and self.speculate and not want_trajectory:
+            main = torch.cuda.current_stream(self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                screen()
+            res = self._rollouts(self.params, self._out, deltas_local, None, False, False, self.step_screen)
+            main.wait_stream(self._side)
             dir_mask = self.mask_local
-        res = self._rollouts(self.params, self._out, deltas_local, dir_mask, self.v2, want_trajectory,
-                             self.step_screen)
+        else:
+            if self.sim_params is not None:
+                screen()
+                dir_mask = self.mask_local
+            res = self._rollouts(self.params, self._out, deltas_local, dir_mask, self.v2, want_trajectory,
+                                 self.step_screen)
         self.last = res
         if res.stats_partial is not None and res.stats_partial is not getattr(self._chunked, "stats_partial", None):
             self._out["stats_partial"] = res.stats_partial  # reuse: iterations allocate nothing

@@ -227,6 +227,38 @@ def test_engine_masked_update_and_resume(S, O):
     assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)) and torch.equal(eng.W, eng2.W)
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_speculative_real_rollouts_equal_screen_first(S, use_graph):
+    """Reward-constraint safe mode, V1: rolling out ALL directions in the real world beside the simulator
+    rollouts and masking afterwards (engine default) is bit-identical to screening first and rolling out the
+    survivors only -- returns (NaN pattern included), mask, survivor count and policy, over several
+    iterations, eagerly and as a replayed graph.  V2 engines and trajectory requests never speculate."""
+    n, N, H, nu = 3, 16, 130, 0.05
+    real = S.make_params(n=n, l_i=.8, m_i=1.2, k=10.2)
+    sim = S.make_params(n=n, l_i=.81, m_i=1.21, k=10.25)
+    W0 = np.random.default_rng(2).uniform(-1, 1, 16) * 0.3
+    probe = S.ArsEngine(sim, N=N, b=N, alpha=0.01, nu=nu, H=H, seed=5, initial_policy=W0, distributed=False)
+    sim_ret = probe.run_iteration(update=False).cpu().numpy()
+    thr = float(np.median(np.minimum(sim_ret[0::2], sim_ret[1::2])))
+    kw = dict(N=N, b=5, alpha=0.01, nu=nu, H=H, seed=5, initial_policy=W0, sim_params=sim, sim_threshold=thr,
+              distributed=False, semantics=S.ARS_TOPB, use_graph=use_graph)
+    spec, first = S.ArsEngine(real, **kw), S.ArsEngine(real, speculate=False, **kw)
+    assert spec.speculate and not first.speculate
+    screened = []
+    for it in range(5):
+        a, b = spec.run_iteration().clone(), first.run_iteration().clone()
+        assert torch.equal(torch.isnan(a), torch.isnan(b)), it
+        screened.append(int(torch.isnan(a).sum()))
+        assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)), it
+        assert torch.equal(spec.mask, first.mask) and torch.equal(spec.W, first.W)
+        assert torch.equal(spec.n_pass_total, first.n_pass_total)
+    assert 0 < screened[0] < 2 * N and (spec._graph is not None) == use_graph
+    # not where a screened-out rollout would leave something behind
+    assert not S.ArsEngine(real, v2=True, **kw).speculate
+    t = spec.run_iteration(want_trajectory=True, update=False)
+    assert torch.equal(torch.isnan(t), torch.isnan(spec.last.returns))  # screened first: the rollout kernel wrote the NaNs
+
+
 def test_estimator_objective(S, O):
     """Estimator.I (ars/estimator.py:36-62): zero at the true parameters (the reference's own
     self-check, estimator.py:136), and equal to the oracle's value elsewhere."""
