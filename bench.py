@@ -593,7 +593,8 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
         return out
 
     KERNEL_TEXT = {"thread": "one thread per environment", "lanes": "lane-split: one environment over %d lanes, one warp per lane group",
-                   "lanes2": "lane-split over %d lanes, two warps per lane group (main + operator warp)"}
+                   "lanes2": "lane-split over %d lanes, two warps per lane group (main + operator warp)",
+                   "lanes3": "lane-split over %d lanes, three warps per lane group (main + two operator warps)"}
 
     def describe(eng, note=""):
         name = S.ops.rollout_kernel_choice(eng.params, eng.B_local, rollouts_per_policy=eng.R)

@@ -11,7 +11,7 @@ All arithmetic runs in libswimmer_ars.so (hand-written sm_100a CUDA); there is n
 """
 from . import _lib, ops  # noqa: F401
 from ._lib import (ARS_AGENT, ARS_RLGLUE, ARS_TOPB, DELTA_01, DELTA_PM1, GYM, KERNEL_AUTO, KERNEL_LANES,  # noqa: F401
-                   KERNEL_LANES2, KERNEL_THREAD, RLGLUE, SwimmerLibError, build_library, make_params)
+                   KERNEL_LANES2, KERNEL_LANES3, KERNEL_THREAD, RLGLUE, SwimmerLibError, build_library, make_params)
 from .ars_agent import ARSAgent  # noqa: F401
 from .database import Database, pick_sub_database  # noqa: F401
 from .engine import ArsEngine  # noqa: F401

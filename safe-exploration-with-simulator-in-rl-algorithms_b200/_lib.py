@@ -17,7 +17,7 @@ GYM, RLGLUE = 0, 1
 POLICY_FIXED_ACTION, POLICY_EXPLICIT, POLICY_PHILOX, POLICY_DELTAS = 0, 1, 2, 3
 DELTA_PM1, DELTA_01 = 0, 1
 ARS_AGENT, ARS_TOPB, ARS_RLGLUE = 0, 1, 2
-KERNEL_AUTO, KERNEL_THREAD, KERNEL_LANES, KERNEL_LANES2 = 0, 1, 2, 3  # swm_rollout_kernel
+KERNEL_AUTO, KERNEL_THREAD, KERNEL_LANES, KERNEL_LANES2, KERNEL_LANES3 = 0, 1, 2, 3, 4  # swm_rollout_kernel
 MIN_SEGMENTS, MAX_SEGMENTS = 2, 10
 ABI_VERSION = 3  # include/swimmer_ars.h SWM_ABI_VERSION
 MAX_MODELS_PER_STEP = 24  # SWM_MAX_MODELS_PER_STEP

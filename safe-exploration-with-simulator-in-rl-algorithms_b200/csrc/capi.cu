@@ -180,7 +180,7 @@ int build_rollout_args(const swm_params_t* params, const swm_rollout_t* cfg, Rol
   if (!params_ok(params) || !cfg) return SWM_ERR_BAD_ARG;
   if (cfg->B < 0 || cfg->H < 0 || cfg->rollouts_per_policy < 1) return SWM_ERR_BAD_ARG;
   if (cfg->variant != SWM_DYN_GYM && cfg->variant != SWM_DYN_RLGLUE) return SWM_ERR_BAD_ARG;
-  if (cfg->kernel < SWM_KERNEL_AUTO || cfg->kernel > SWM_KERNEL_LANES2) return SWM_ERR_BAD_ARG;
+  if (cfg->kernel < SWM_KERNEL_AUTO || cfg->kernel > SWM_KERNEL_LANES3) return SWM_ERR_BAD_ARG;
   if (cfg->B > (int64_t)kRolloutBlock * 0x7fffffffLL) return SWM_ERR_BAD_ARG;
   memset(&a, 0, sizeof(a));
   f.variant = cfg->variant;
@@ -246,19 +246,26 @@ int build_rollout_args(const swm_params_t* params, const swm_rollout_t* cfg, Rol
 
 // AUTO (measured crossovers, tools/lane_split_sweep.py, profiles/r02_summary.md), for chains of up to 7 segments
 // (8 lanes per environment):
+//   lane groups <= 1 per SM, n >= 6       -> LANES3: main warp + two operator warps taking alternate steps (the
+//                                            operator warp is the slower one of the pair from 6 segments on;
+//                                            n = 7: 683 against 802 cycles per step, n <= 5: no gain)
 //   lane groups <= 2 per SM               -> LANES2: main warp + operator warp per group, every warp on a
 //                                            sub-partition of its own (n = 5: 0.30 ms against 0.40 / 0.72 ms)
 //   lane-split warps <= 2 per sub-partition -> LANES (n = 5, 2,048 envs: 0.42 ms against 0.72 ms)
 //   larger batches                        -> THREAD (one environment per thread fills the FP64 units)
 constexpr double kLaneSplitMaxWarpsPerSmsp = 2.0;
 constexpr double kLane2MaxGroupsPerSm = 2.0;
+constexpr int kLane3MinSegments = 6;
+
+inline bool is_lane_kernel(int k) { return k == SWM_KERNEL_LANES || k == SWM_KERNEL_LANES2 || k == SWM_KERNEL_LANES3; }
 
 int choose_kernel(int n, const swm_rollout_t* cfg, const RolloutArgs& a, const RolloutFlags& f) {
   const bool ok = lane_split_supported(a, f);
-  if (cfg->kernel == SWM_KERNEL_LANES || cfg->kernel == SWM_KERNEL_LANES2) return ok ? cfg->kernel : SWM_ERR_UNSUPPORTED;
+  if (is_lane_kernel(cfg->kernel)) return ok ? cfg->kernel : SWM_ERR_UNSUPPORTED;
   if (cfg->kernel == SWM_KERNEL_THREAD || !ok || n > 7) return SWM_KERNEL_THREAD;
   const int per_warp = 32 / lane_split_lanes(n);
   const double groups = (double)((cfg->B + per_warp - 1) / per_warp);
+  if (n >= kLane3MinSegments && groups <= sm_count_cached()) return SWM_KERNEL_LANES3;
   if (groups <= kLane2MaxGroupsPerSm * sm_count_cached()) return SWM_KERNEL_LANES2;
   return groups <= kLaneSplitMaxWarpsPerSmsp * 4.0 * sm_count_cached() ? SWM_KERNEL_LANES : SWM_KERNEL_THREAD;
 }
@@ -455,7 +462,7 @@ extern "C" int64_t swm_rollout_stats_blocks(const swm_params_t* params, const sw
   RolloutFlags f;
   if (build_rollout_args(params, &probe, a, f) != SWM_OK) return 0;
   const int kernel = choose_kernel(params->n, &probe, a, f);
-  if (kernel == SWM_KERNEL_LANES || kernel == SWM_KERNEL_LANES2) {
+  if (is_lane_kernel(kernel)) {
     const int per_warp = 32 / lane_split_lanes(params->n);
     return (cfg->B + per_warp - 1) / per_warp;
   }
@@ -481,8 +488,8 @@ extern "C" int swm_rollout(const swm_params_t* params, const swm_rollout_t* cfg,
   const int kernel = choose_kernel(params->n, cfg, a, f);
   if (kernel < 0) return kernel;
   cudaStream_t st = (cudaStream_t)stream;
-  if (kernel == SWM_KERNEL_LANES || kernel == SWM_KERNEL_LANES2) {
-#define CALL(K) launch_lane_rollout_n<K>(a, f, kernel == SWM_KERNEL_LANES2, st)
+  if (is_lane_kernel(kernel)) {
+#define CALL(K) launch_lane_rollout_n<K>(a, f, kernel == SWM_KERNEL_LANES3 ? 2 : kernel == SWM_KERNEL_LANES2 ? 1 : 0, st)
     SWM_DISPATCH_N(params->n, CALL)
 #undef CALL
   }

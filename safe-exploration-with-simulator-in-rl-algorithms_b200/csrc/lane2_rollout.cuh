@@ -38,9 +38,13 @@ constexpr int kLane2Block = 64;
 __device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-template <int N, bool LINEAR, bool NORM, bool STATS>
-__global__ void __launch_bounds__(kLane2Block)
+// NF = number of operator warps (1 or 2).  With two, warp 1 forms the rows of the even steps and warp 2 those of
+// the odd steps (each owns one parity of the (sin, cos) / row buffers and of the barrier ids, so nothing else
+// changes): a row set is then due every second step of M instead of every step.
+template <int N, bool LINEAR, bool NORM, bool STATS, int NF = 1>
+__global__ void __launch_bounds__(32 * (1 + NF))
 lane2_rollout_kernel(const RolloutArgs a) {
+  static_assert(NF == 1 || NF == 2, "one or two operator warps");
   constexpr int L = LaneSplit<N>::L, G = LaneSplit<N>::G;
   constexpr int NO = 2 * N + 2, NA = N - 1, WS = NA * NO, J = N - 1;
   constexpr int NV = 7 * J - 4 > 0 ? 7 * J - 4 : 3;  // X_j (3 each, j = 1..J) then T_j (4 each, j = 2..J)
@@ -91,7 +95,7 @@ lane2_rollout_kernel(const RolloutArgs a) {
     }
   }
 
-  if (warp == 1) {
+  if (warp >= 1) {
     // =========================================== warp F ===========================================
     // A pure function of the angles: (sin, cos) of every segment at step u  ->  this lane's row y_i(u) of the
     // solution operator.  Every lane reads all N (sin, cos) pairs M published (no exchange inside this warp),
@@ -180,12 +184,18 @@ lane2_rollout_kernel(const RolloutArgs a) {
     };
     // one row set per step u = 0 .. H-1 (M publishes the angles of step u+1 during step u, those of step 0
     // before its loop)
-    int u = 0;
-    for (; u + 1 < a.H; u += 2) {
-      frow(std::integral_constant<int, 0>());
-      frow(std::integral_constant<int, 1>());
+    if (NF == 1) {
+      int u = 0;
+      for (; u + 1 < a.H; u += 2) {
+        frow(std::integral_constant<int, 0>());
+        frow(std::integral_constant<int, 1>());
+      }
+      if (u < a.H) frow(std::integral_constant<int, 0>());
+    } else if (warp == 1) {
+      for (int u = 0; u < a.H; u += 2) frow(std::integral_constant<int, 0>());
+    } else {
+      for (int u = 1; u < a.H; u += 2) frow(std::integral_constant<int, 1>());
     }
-    if (u < a.H) frow(std::integral_constant<int, 0>());
     return;
   }
 
@@ -290,16 +300,9 @@ lane2_rollout_kernel(const RolloutArgs a) {
       rotate_by(sn, cm1, sN, cN);
       const bool resync = (t & 63) == 63;
       const bool slow = resync || hi > kRotateShortHi;
-      if (__any_sync(FULL, slow)) {
-        if (slow) {
-          if (resync || hi > kRotateLongHi) {
-            sincos(th, &sN, &cN);
-          } else {
-            small_sincos_tail(d, z, sn, cm1);
-            sN = s; cN = c;
-            rotate_by(sn, cm1, sN, cN);
-          }
-        }
+      if (__any_sync(FULL, slow)) {  // out of line: see tracked_sincos_slow
+        const double2 r = tracked_sincos_slow(th, d, s, c, resync || hi > kRotateLongHi);
+        if (slow) { sN = r.x; cN = r.y; }
       }
     }
     if (t + 1 < a.H) {

@@ -17,31 +17,33 @@ inline bool lane_split_supported(const RolloutArgs& a, const RolloutFlags& f) {
   return !(f.stats && !f.norm);
 }
 
-// two_warps: the warp-specialised form (lane2_rollout.cuh: main warp + factorisation warp per lane group)
-template <int N> int launch_lane_rollout_n(const RolloutArgs& a, const RolloutFlags& f, bool two_warps, cudaStream_t st);
+// f_warps: 0 = one warp per lane group (lane_rollout.cuh); 1 / 2 = the warp-specialised form with that many
+// operator warps beside the main warp (lane2_rollout.cuh)
+template <int N> int launch_lane_rollout_n(const RolloutArgs& a, const RolloutFlags& f, int f_warps, cudaStream_t st);
 
 #ifdef SWM_INSTANTIATE_LANE_N
 
 template <int N, bool LINEAR, bool NORM, bool STATS>
-static int launch_lane_one(const RolloutArgs& a, bool two_warps, cudaStream_t st) {
+static int launch_lane_one(const RolloutArgs& a, int f_warps, cudaStream_t st) {
   constexpr int G = LaneSplit<N>::G;
   const long long blocks = (a.B + G - 1) / G;
   if (blocks > 0x7fffffffLL) return SWM_ERR_BAD_ARG;
-  if (two_warps) lane2_rollout_kernel<N, LINEAR, NORM, STATS><<<(unsigned)blocks, kLane2Block, 0, st>>>(a);
+  if (f_warps == 2) lane2_rollout_kernel<N, LINEAR, NORM, STATS, 2><<<(unsigned)blocks, 96, 0, st>>>(a);
+  else if (f_warps == 1) lane2_rollout_kernel<N, LINEAR, NORM, STATS, 1><<<(unsigned)blocks, 64, 0, st>>>(a);
   else lane_rollout_kernel<N, LINEAR, NORM, STATS><<<(unsigned)blocks, kLaneBlock, 0, st>>>(a);
   return cudaPeekAtLastError() == cudaSuccess ? SWM_OK : SWM_ERR_CUDA;
 }
 
 template <int N>
-int launch_lane_rollout_n(const RolloutArgs& a, const RolloutFlags& f, bool two_warps, cudaStream_t st) {
+int launch_lane_rollout_n(const RolloutArgs& a, const RolloutFlags& f, int f_warps, cudaStream_t st) {
   if (!lane_split_supported(a, f)) return SWM_ERR_UNSUPPORTED;
-  if (!f.linear) return launch_lane_one<N, false, false, false>(a, two_warps, st);
-  if (f.norm && f.stats) return launch_lane_one<N, true, true, true>(a, two_warps, st);
-  if (f.norm) return launch_lane_one<N, true, true, false>(a, two_warps, st);
-  return launch_lane_one<N, true, false, false>(a, two_warps, st);
+  if (!f.linear) return launch_lane_one<N, false, false, false>(a, f_warps, st);
+  if (f.norm && f.stats) return launch_lane_one<N, true, true, true>(a, f_warps, st);
+  if (f.norm) return launch_lane_one<N, true, true, false>(a, f_warps, st);
+  return launch_lane_one<N, true, false, false>(a, f_warps, st);
 }
 
-template int launch_lane_rollout_n<SWM_INSTANTIATE_LANE_N>(const RolloutArgs&, const RolloutFlags&, bool, cudaStream_t);
+template int launch_lane_rollout_n<SWM_INSTANTIATE_LANE_N>(const RolloutArgs&, const RolloutFlags&, int, cudaStream_t);
 
 #endif  // SWM_INSTANTIATE_LANE_N
 

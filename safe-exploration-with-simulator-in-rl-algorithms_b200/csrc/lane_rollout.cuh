@@ -58,6 +58,24 @@ __device__ __forceinline__ double2 lds2(uint32_t addr, int off) {
   return v;
 }
 
+// Rare tiers of the tracked sine/cosine (tail polynomial, exact re-evaluation), out of line, for the main warp of
+// the two-warp kernel (lane2_rollout.cuh): its step loop takes them under a warp-uniform vote, and inlined they put
+// a reconvergence barrier and a taken branch over ~100 instructions into EVERY step (~37 of 570 cycles, ncu source
+// page; n = 3: 498 -> 450 cycles per step).  All lanes call it together; the caller keeps the result only on the
+// lanes that need it.  (The single-warp kernel below keeps them inline: measured 1-3 % faster there.)
+static __device__ __noinline__ double2 tracked_sincos_slow(double th_new, double d, double s, double c, bool exact) {
+  double sN = s, cN = c;
+  if (exact) {
+    sincos(th_new, &sN, &cN);
+  } else {
+    double z, sn, cm1;
+    small_sincos_base(d, z, sn, cm1);
+    small_sincos_tail(d, z, sn, cm1);
+    rotate_by(sn, cm1, sN, cN);
+  }
+  return make_double2(sN, cN);
+}
+
 // Sum of v over the L lanes of an environment by xor butterfly.  Both partners of a level add the same two
 // values, so every lane ends with the bitwise identical sum (Gdot is replicated per lane and must stay so).
 template <int L>

@@ -45,7 +45,8 @@ def rollout_kernel_choice(params, B, *, fixed_actions=False, rollouts_per_policy
     cfg.H, cfg.B, cfg.rollouts_per_policy, cfg.kernel = 1, int(B), int(rollouts_per_policy), int(kernel)
     k = _lib.lib().swm_rollout_kernel_choice(ctypes.byref(params), ctypes.byref(cfg))
     _lib.check(min(k, 0))
-    return {_lib.KERNEL_THREAD: "thread", _lib.KERNEL_LANES: "lanes", _lib.KERNEL_LANES2: "lanes2"}[k]
+    return {_lib.KERNEL_THREAD: "thread", _lib.KERNEL_LANES: "lanes", _lib.KERNEL_LANES2: "lanes2",
+            _lib.KERNEL_LANES3: "lanes3"}[k]
 
 
 def reset_state(n, variant=GYM, device="cuda"):

@@ -39,15 +39,15 @@ def main():
         print("n=%d  V2 + moments, Philox policies, H=%d" % (n, H))
         for B in [int(x) for x in os.environ.get("SWEEP_B", "64,256,512,1024,2048,4096,8192,16384,32768").split(",")]:
             row = []
-            for kern in (S.KERNEL_THREAD, S.KERNEL_LANES, S.KERNEL_LANES2):
+            for kern in (S.KERNEL_THREAD, S.KERNEL_LANES, S.KERNEL_LANES2, S.KERNEL_LANES3):
                 out = {}
                 fn = lambda: S.ops.rollout(p, H, B=B, base_policy=W, nu=0.01, seed=1, mean=mean, inv_sigma=inv,
                                            stats_pivot=piv, kernel=kern, out=out)
                 r = fn()
                 out.update(returns=r.returns, stats_partial=r.stats_partial)
                 row.append(time_ms(fn))
-            print("  B=%6d  thread %.4f ms   lanes %.4f ms   lanes2 %.4f ms   (%.0f / %.0f / %.0f cycles per step @1.965 GHz)"
-                  % (B, row[0], row[1], row[2], row[0] * 1965, row[1] * 1965, row[2] * 1965))
+            print("  B=%6d  thread %.4f ms   lanes %.4f ms   lanes2 %.4f ms   lanes3 %.4f ms   (%.0f / %.0f / %.0f / %.0f cycles per "
+                  "step @1.965 GHz)" % (B, row[0], row[1], row[2], row[3], row[0] * 1965, row[1] * 1965, row[2] * 1965, row[3] * 1965))
 
 
 if __name__ == "__main__":

@@ -38,7 +38,7 @@ def main(ns=(2, 3, 4, 5, 6, 7, 8, 9, 10)):
             S.ops.rollout(p, H, B=Bp, variant=S.RLGLUE, base_policy=W, nu=0.05, seed=3, rollouts_per_policy=R,
                           clip_actions=True, delta_dist=S.DELTA_01)
         # the three rollout kernels forced (AUTO picks by batch size): fixed actions, V1, V2 + moments, trajectories
-        for kern in (S._lib.KERNEL_THREAD, S._lib.KERNEL_LANES, S._lib.KERNEL_LANES2):
+        for kern in (S._lib.KERNEL_THREAD, S._lib.KERNEL_LANES, S._lib.KERNEL_LANES2, S._lib.KERNEL_LANES3):
             S.ops.rollout(p, H, actions=ac, want_final=True, want_trajectory=True, kernel=kern)
             S.ops.rollout(p, H, B=2 * 9, base_policy=W, nu=0.05, seed=3, want_final=True, kernel=kern)
             r = S.ops.rollout(p, H, B=2 * 5 * 3, base_policy=W, nu=0.05, seed=3, rollouts_per_policy=3, init_perturb=1e-2,
