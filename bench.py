@@ -600,8 +600,12 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
         name = S.ops.rollout_kernel_choice(eng.params, eng.B_local, rollouts_per_policy=eng.R)
         lanes = 32 // S.ops.lane_split_envs_per_warp(eng.params.n)
         text = KERNEL_TEXT[name] % lanes if "%d" in KERNEL_TEXT[name] else KERNEL_TEXT[name]
-        return {"launch": "CUDA graph replay" if eng._graph is not None else "eager",
-                "exchange": eng.exchange.transport, "rollout_kernel": text + note, "envs_per_gpu": eng.B_local}
+        out = {"launch": "CUDA graph replay" if eng._graph is not None else "eager",
+               "exchange": eng.exchange.transport, "rollout_kernel": text + note, "envs_per_gpu": eng.B_local}
+        if eng.replicated:
+            out["sharding"] = ("replicated on every rank, no exchange (ArsEngine shard='auto': the whole batch already runs on "
+                               "the latency-optimised kernel, a smaller share per GPU would not be faster)")
+        return out
 
     # ---------------- config[2]: ARS V2, n = 5, 1,024 directions ----------------
     if 1024 % world == 0:
@@ -667,7 +671,7 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
             barrier()
             t = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
             npass = torch.tensor([float(int(eng.n_pass_total.cpu()[0]) - pass0)], dtype=torch.float64, device=device)
-            if world > 1:
+            if world > 1 and not eng.replicated:
                 dist.all_reduce(npass)
             return t, float(npass.cpu()[0]) / (K * 256.0), eng.check_exchange()
 
@@ -684,7 +688,8 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
         res["config[3]"] = dict(
             workload="config[3]: safe-exploration ARS V1 (reward constraint), 3-segment swimmer, 256 directions: 512 simulator "
                      "rollouts screen every +-delta pair, surviving pairs are rolled out in the real world; real (l,m,k) = "
-                     "(0.8,1.2,10.2), simulator = real + 1e-3 u/|u|, pre-trained W0; sharded over %d GPU(s)" % world,
+                     "(0.8,1.2,10.2), simulator = real + 1e-3 u/|u|, pre-trained W0; %s %d GPU(s)"
+                     % ("replicated on each of" if eng.replicated else "sharded over", world),
             iters_per_s=K / t, ms_per_iter=1e3 * t / K, env_steps_per_s=K * steps / t, iters_timed=K,
             screened_fraction=1.0 - frac_pass, sim_threshold=thr,
             schedule="speculative (engine default for V1 safe mode): the real-world rollouts of all 256 directions run beside "
@@ -699,7 +704,8 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
             exchange_epochs=ee, parity_vs_single=par,
             roofline={"bound": "latency (512 + 512 envs side by side)",
                       "executed": {"flops_per_env_step": EXEC_FLOPS["n3_v1"],
-                                   "frac": (K * steps / t / world) * EXEC_FLOPS["n3_v1"] / 1e12 / fp64_peak_tflops}},
+                                   "frac": (K * steps / t / (1 if eng.replicated else world)) * EXEC_FLOPS["n3_v1"] / 1e12
+                                   / fp64_peak_tflops}},
             **describe(eng))
         eng.exchange.close()
         del eng

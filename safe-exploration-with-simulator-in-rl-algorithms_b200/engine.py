@@ -36,7 +36,7 @@ class ArsEngine:
                  clip_actions=False, init_perturb=0.0, initial_policy=None, group=None,
                  distributed=None, device=None, sim_params=None, sim_threshold=None,
                  step_screen=None, use_graph=False, curve_capacity=0, rollout_chunks=None, transport="auto",
-                 rollout_kernel=0, speculate=True):
+                 rollout_kernel=0, speculate=True, shard="auto"):
         _lib.require_cuda()
         self.params, self.N, self.b, self.alpha, self.nu, self.H = params, int(N), int(b), alpha, nu, int(H)
         self.v2, self.semantics, self.R = bool(v2), semantics, int(rollouts_per_direction)
@@ -47,6 +47,18 @@ class ArsEngine:
             "cuda", torch.cuda.current_device())
         self.group = group
         use_dist = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        # shard="auto": a problem whose WHOLE batch already runs on the latency-optimised kernels (two / three warps
+        # per lane group, every warp alone on an SM sub-partition) does not get faster on fewer environments per GPU
+        # -- the rollout is one dependent chain of H steps either way -- and sharding it only adds the exchange.
+        # Such engines run replicated: every rank computes all N directions, bit-identically, with no exchange.
+        # shard=True always shards over the process group.
+        self.replicated = False
+        if use_dist and shard == "auto" and dist.get_world_size(group) > 1:
+            with torch.cuda.device(self.device):
+                whole = ops.rollout_kernel_choice(params, 2 * self.N * self.R, rollouts_per_policy=self.R,
+                                                  kernel=int(rollout_kernel))
+            if variant == GYM and not clip_actions and step_screen is None and whole in ("lanes2", "lanes3"):
+                use_dist, self.replicated = False, True
         self.world = dist.get_world_size(group) if use_dist else 1
         self.rank = dist.get_rank(group) if use_dist else 0
         if self.N % self.world != 0:

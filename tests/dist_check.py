@@ -38,7 +38,8 @@ def main():
             if safe:
                 kw.update(sim_params=S.make_params(n=n, l_i=1.001, m_i=0.999, k=10.01), sim_threshold=0.0,
                           initial_policy=torch.linspace(-0.3, 0.3, (n - 1) * (2 * n + 2)))
-            eng = S.ArsEngine(p, transport=transport, use_graph=use_graph, **kw)   # sharded
+            eng = S.ArsEngine(p, transport=transport, use_graph=use_graph, shard=True, **kw)   # sharded (forced: these
+            # batches are small enough for shard="auto" to run them replicated, see below)
             ref = S.ArsEngine(p, distributed=False, **kw)                          # the whole problem alone
             assert eng.exchange.transport == transport and eng.world == world, (eng.exchange.transport, transport)
             for it in range(4):
@@ -70,6 +71,18 @@ def main():
             if rank == 0:
                 print("dist_check ok: %s graph=%s n=%d v2=%s semantics=%d R=%d safe=%s world=%d"
                       % (transport, use_graph, n, v2, sem, R, safe, world), flush=True)
+    # shard="auto": a batch that is latency-bound as a whole is not sharded; every rank runs all of it, no exchange
+    p = S.make_params(n=3)
+    kw = dict(N=16, b=5, alpha=0.02, nu=0.03, H=150, semantics=S.ARS_TOPB, seed=42, device=device)
+    auto, ref = S.ArsEngine(p, use_graph=True, **kw), S.ArsEngine(p, distributed=False, **kw)
+    assert auto.replicated and auto.world == 1 and auto.exchange.transport == "local"
+    for it in range(3):
+        assert torch.equal(auto.run_iteration(), ref.run_iteration()) and torch.equal(auto.W, ref.W)
+    big = S.ArsEngine(S.make_params(n=5), N=1024, b=8, alpha=0.02, nu=0.03, H=10, v2=True, seed=1, device=device)
+    assert not big.replicated and big.world == world      # config[2] is sharded: its share runs on a faster kernel
+    big.exchange.close()
+    if rank == 0:
+        print("dist_check ok: shard=auto replicates the latency-bound batch, shards config[2]", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -16,7 +16,7 @@ def _run(world, port):
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check.py")]
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=420)
     assert out.returncode == 0, out.stdout[-4000:]
-    assert out.stdout.count("dist_check ok") == 8, out.stdout[-4000:]
+    assert out.stdout.count("dist_check ok") == 9, out.stdout[-4000:]   # 2 transports x 4 cases + the shard="auto" check
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
