@@ -27,8 +27,8 @@ sys.path.insert(0, ROOT)
 N_SEG, B_PER_GPU, H = 3, 65536, 1000
 W_REF = {3: 822, 5: 1751, 10: 5701}        # algorithmic flops per env-step
 W_REF_V2 = {3: 838, 5: 1775, 10: 5745}
-# Measured once per kernel change with ncu (profiles/r01c_summary.md, profiles/r02_summary.md):
-NCU_DRAM_BYTES_PER_LAUNCH = 1.07e6          # config[1] kernel: dram__bytes_read.sum + dram__bytes_write.sum
+# Measured once per kernel change with ncu (profiles/r02_summary.md, final-build captures r02z_*):
+NCU_DRAM_BYTES_PER_LAUNCH = 1.073e6         # config[1] kernel: dram__bytes_read.sum + dram__bytes_write.sum
 # FP64 flops one environment step costs in the one-thread-per-environment kernels (2 per DFMA, 1 per DADD/DMUL,
 # ncu source-page instruction counts / 32 lanes): the non-redundant work of a step
 EXEC_FLOPS = {"n3_fixed": 312.0, "n3_v1": 344.0, "n5_v2": 735.0, "n10_v2": 1800.0}
@@ -507,11 +507,11 @@ def run_b200(args):
                          "frac": exec_tf / fp64_peak_tflops, "flops_per_env_step": EXEC_FLOPS["n3_fixed"],
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
-                                         "profiles/r01c_n3_fixed_ncu.csv): ~0 B per env-step, not HBM-bound",
+                                         "profiles/r02z_n3_fixed_plain_ncu.csv): ~0 B per env-step, not HBM-bound",
                          "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 "
                                         "entry; nominal 37.2 TFLOP/s)",
                          "note": "achieved = per-GPU env-steps/s x 312 FP64 flops the O(n) kernel EXECUTES per env-step "
-                                 "(ncu instruction counts, profiles/r01c_summary.md); a DFMA with three register sources "
+                                 "(ncu instruction counts, profiles/r02_summary.md); a DFMA with three register sources "
                                  "issues every 3.1 cycles on B200, so the pipe saturates below 1.0",
                          "algorithmic": {"flops_per_env_step": W_REF[N_SEG], "achieved": per_gpu * W_REF[N_SEG] / 1e12,
                                          "frac": per_gpu * W_REF[N_SEG] / 1e12 / fp64_peak_tflops,
