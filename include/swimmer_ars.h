@@ -310,7 +310,8 @@ typedef struct {
   const double* returns_local;  /* [2 n_local R] per-env returns of this rank's rollouts */
   int32_t n_local;              /* directions owned by this rank */
   int32_t rollouts_per_policy;  /* R: record carries the mean over the R rollouts of a policy */
-  const int32_t* mask_local;    /* [n_local] or NULL: screening mask of this rank's directions */
+  const int32_t* mask_local;    /* [n_local] or NULL: screening mask of this rank's directions; the returns of a
+                                   direction with mask 0 are packed as NaN whether or not its rollouts ran */
   const double* stats_partial;  /* [n_blocks, 2, F] from swm_rollout, or NULL (count 0) */
   int64_t n_blocks;
   int32_t n_features;           /* F = 2n+2, or 0 for ARS V1 (no statistics in the record) */

@@ -459,6 +459,16 @@ def test_pack_exchange_kernel_matches_separate_kernels(S, R, with_mask, v2):
     assert torch.equal(torch.isnan(returns_all), torch.isnan(want_r))
     if with_mask:
         assert torch.equal(mask_all, mask)
+        # returns of a screened-out direction are NaN in the record even when its rollouts did run (the engine's
+        # speculative real-world rollouts): same result from unmasked rollouts + the mask
+        full = S.ops.rollout(p, H, B=2 * Nl * R, base_policy=W, nu=0.05, seed=3, rollouts_per_policy=R,
+                             mean=mean if v2 else None, inv_sigma=inv if v2 else None)
+        assert not bool(torch.isnan(full.returns).any())
+        r2 = torch.zeros(2 * Nl, **f64)
+        S.ops.pack_exchange(None, returns_local=full.returns, n_local=Nl, R=R, mask_local=mask, n_features=0,
+                            returns_all=r2, mask_all=torch.zeros(Nl, dtype=torch.int32, device="cuda"))
+        assert torch.equal(torch.isnan(r2), torch.isnan(returns_all))
+        assert torch.equal(torch.nan_to_num(r2), torch.nan_to_num(returns_all))
     if v2:
         want_rec = S.ops.stats_finalize(res.stats_partial, samples, piv, units=units)
         np.testing.assert_allclose(records[0].cpu().numpy(), want_rec.cpu().numpy(), rtol=1e-12, atol=1e-13)
