@@ -602,6 +602,10 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
         text = KERNEL_TEXT[name] % lanes if "%d" in KERNEL_TEXT[name] else KERNEL_TEXT[name]
         out = {"launch": "CUDA graph replay" if eng._graph is not None else "eager",
                "exchange": eng.exchange.transport, "rollout_kernel": text + note, "envs_per_gpu": eng.B_local}
+        if eng.shard_replicas > 1:
+            out["sharding"] = ("sharded over blocks of %d GPUs, %d blocks each running the whole problem (ArsEngine shard='auto': "
+                               "a share smaller than one lane group per SM is not faster, more peers only lengthen the exchange)"
+                               % (eng.world, eng.shard_replicas))
         if eng.replicated:
             out["sharding"] = ("replicated on every rank, no exchange (ArsEngine shard='auto': the whole batch already runs on "
                                "the latency-optimised kernel, a smaller share per GPU would not be faster)")
@@ -621,13 +625,14 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
         ee = eng.check_exchange()
         res["config[2]"] = dict(
             workload="config[2]: ARS V2 (obs normalisation), 5-segment swimmer, 1,024 directions (2,048 rollouts), H=1000; "
-                     "directions sharded over %d GPU(s) (strong scaling)" % world,
+                     "directions sharded over %d GPU(s)%s (strong scaling)"
+                     % (eng.world, " in each of %d blocks of the %d" % (eng.shard_replicas, world) if eng.shard_replicas > 1 else ""),
             iters_per_s=K / t, ms_per_iter=1e3 * t / K, env_steps_per_s=K * steps / t, iters_timed=K,
             mean_return_last=float(eng.returns.mean().cpu()), exchange_epochs=ee, parity_vs_single=par,
             roofline={"bound": "latency (2,048 envs in all: at most one lane-split warp per SM sub-partition)",
                       "executed": {"flops_per_env_step": EXEC_FLOPS["n5_v2"],
-                                   "frac": (K * steps / t / world) * EXEC_FLOPS["n5_v2"] / 1e12 / fp64_peak_tflops},
-                      "algorithmic_frac": (K * steps / t / world) * W_REF_V2[5] / 1e12 / fp64_peak_tflops},
+                                   "frac": (K * steps / t / eng.world) * EXEC_FLOPS["n5_v2"] / 1e12 / fp64_peak_tflops},
+                      "algorithmic_frac": (K * steps / t / eng.world) * W_REF_V2[5] / 1e12 / fp64_peak_tflops},
             **describe(eng))
         eng.exchange.close()
         del eng

@@ -52,13 +52,26 @@ class ArsEngine:
         # -- the rollout is one dependent chain of H steps either way -- and sharding it only adds the exchange.
         # Such engines run replicated: every rank computes all N directions, bit-identically, with no exchange.
         # shard=True always shards over the process group.
-        self.replicated = False
+        self.replicated, self.shard_replicas = False, 1
         if use_dist and shard == "auto" and dist.get_world_size(group) > 1:
             with torch.cuda.device(self.device):
                 whole = ops.rollout_kernel_choice(params, 2 * self.N * self.R, rollouts_per_policy=self.R,
                                                   kernel=int(rollout_kernel))
             if variant == GYM and not clip_actions and step_screen is None and whole in ("lanes2", "lanes3"):
                 use_dist, self.replicated = False, True
+            elif group is None and variant == GYM and not clip_actions and step_screen is None:
+                # ... and it is sharded only as far as that helps: over the smallest number of ranks S whose share runs
+                # on those kernels with at most one lane group per SM; the world/S blocks of S consecutive ranks then
+                # each run the whole problem (config[2] on 8 GPUs: 2 blocks of 4, the exchange has 4 peers not 8)
+                W = dist.get_world_size()
+                S = self._useful_shards(params, W, rollout_kernel)
+                if S < W:
+                    me = dist.get_rank()
+                    for blk in range(W // S):
+                        g = dist.new_group(list(range(blk * S, (blk + 1) * S)))
+                        if me // S == blk:
+                            group = g
+                    self.group, self.shard_replicas = group, W // S
         self.world = dist.get_world_size(group) if use_dist else 1
         self.rank = dist.get_rank(group) if use_dist else 0
         if self.N % self.world != 0:
@@ -131,6 +144,19 @@ class ArsEngine:
             self._chunked = ops.ChunkedRollout(
                 params, self.H, B=Bl, n_sub=n_sub, chunk=chunk, variant=self.variant, base_policy=self.W,
                 rollouts_per_policy=self.R, stats_pivot=self.pivot if self.v2 else None, device=self.device, **kw)
+
+    def _useful_shards(self, params, world, rollout_kernel):
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        per_warp = ops.lane_split_envs_per_warp(params.n)
+        with torch.cuda.device(self.device):
+            for cand in range(2, world):
+                if world % cand or self.N % cand:
+                    continue
+                share = 2 * self.N * self.R // cand
+                name = ops.rollout_kernel_choice(params, share, rollouts_per_policy=self.R, kernel=int(rollout_kernel))
+                if name in ("lanes2", "lanes3") and (share + per_warp - 1) // per_warp <= sms:
+                    return cand
+        return world
 
     # -------------------------------------------------------------------------------------------
     def _rollouts(self, params, out, deltas_local, dir_mask, want_stats, want_trajectory, screen):
