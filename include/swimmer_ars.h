@@ -80,7 +80,8 @@ typedef enum {
   SWM_KERNEL_THREAD = 1, /* one thread = one environment (throughput: BASELINE configs 2 and 5) */
   SWM_KERNEL_LANES = 2,  /* one environment spread over 4/8/16 lanes, lane = segment (latency: the 2,048-env
                             ARS iteration of config 3, the 512-env safe-exploration rollouts of config 4);
-                            gym dynamics without per-step screening / clipping, else SWM_ERR_UNSUPPORTED */
+                            gym dynamics without per-step screening / clipping, else SWM_ERR_UNSUPPORTED
+                            (LANES2 / LANES3 also run per-step screening of plain linear policies) */
   SWM_KERNEL_LANES2 = 3, /* LANES cut into two warps per lane group (main warp + factorisation warp on separate
                             SM sub-partitions): batches so small that sub-partitions would otherwise idle */
   SWM_KERNEL_LANES3 = 4  /* LANES2 with two factorisation warps taking alternate steps: the smallest batches */

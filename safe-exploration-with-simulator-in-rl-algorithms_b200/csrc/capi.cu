@@ -260,13 +260,15 @@ constexpr int kLane3MinSegments = 6;
 inline bool is_lane_kernel(int k) { return k == SWM_KERNEL_LANES || k == SWM_KERNEL_LANES2 || k == SWM_KERNEL_LANES3; }
 
 int choose_kernel(int n, const swm_rollout_t* cfg, const RolloutArgs& a, const RolloutFlags& f) {
-  const bool ok = lane_split_supported(a, f);
+  // per-step screening exists in the warp-specialised kernels only
+  const bool ok = lane_split_supported(a, f, cfg->kernel == SWM_KERNEL_LANES ? 0 : 1);
   if (is_lane_kernel(cfg->kernel)) return ok ? cfg->kernel : SWM_ERR_UNSUPPORTED;
   if (cfg->kernel == SWM_KERNEL_THREAD || !ok || n > 7) return SWM_KERNEL_THREAD;
   const int per_warp = 32 / lane_split_lanes(n);
   const double groups = (double)((cfg->B + per_warp - 1) / per_warp);
   if (n >= kLane3MinSegments && groups <= sm_count_cached()) return SWM_KERNEL_LANES3;
   if (groups <= kLane2MaxGroupsPerSm * sm_count_cached()) return SWM_KERNEL_LANES2;
+  if (f.screen) return SWM_KERNEL_THREAD;
   return groups <= kLaneSplitMaxWarpsPerSmsp * 4.0 * sm_count_cached() ? SWM_KERNEL_LANES : SWM_KERNEL_THREAD;
 }
 

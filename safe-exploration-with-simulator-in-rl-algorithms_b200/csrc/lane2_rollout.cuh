@@ -41,17 +41,23 @@ __device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arr
 // NF = number of operator warps (1 or 2).  With two, warp 1 forms the rows of the even steps and warp 2 those of
 // the odd steps (each owns one parity of the (sin, cos) / row buffers and of the barrier ids, so nothing else
 // changes): a row set is then due every second step of M instead of every step.
-template <int N, bool LINEAR, bool NORM, bool STATS, int NF = 1>
+// SCREEN = per-step state-constraint screening (Safe_ARS.rollout, safe_ars/ars.py:124-153; see rollout_kernel): before
+// a step is taken, one step of the simulator model from the same state is judged by max_i |thd_i| <= sim_thresh.  In
+// the non-dimensional form the joint matrix only depends on the angles, so the simulator's accelerations are a second
+// right-hand side dotted with the SAME solution rows; an environment judged unsafe freezes for the rest of the horizon
+// (its lanes keep taking part in the exchanges, nothing of it advances).
+template <int N, bool LINEAR, bool NORM, bool STATS, int NF = 1, bool SCREEN = false>
 __global__ void __launch_bounds__(32 * (1 + NF))
 lane2_rollout_kernel(const RolloutArgs a) {
   static_assert(NF == 1 || NF == 2, "one or two operator warps");
+  static_assert(!SCREEN || (LINEAR && !NORM && !STATS), "screening: plain linear policies only");
   constexpr int L = LaneSplit<N>::L, G = LaneSplit<N>::G;
   constexpr int NO = 2 * N + 2, NA = N - 1, WS = NA * NO, J = N - 1;
   constexpr int NV = 7 * J - 4 > 0 ? 7 * J - 4 : 3;  // X_j (3 each, j = 1..J) then T_j (4 each, j = 2..J)
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int kRow = 32 * 16;
   // rows of one double2 per lane; + parity where noted
-  enum { ROW_OBS = 0, ROW_T = 1, ROW_R = 2, ROW_PSI = 3, ROW_SC = 4, ROWS = 6 };  // SC: + parity
+  enum { ROW_OBS = 0, ROW_T = 1, ROW_R = 2, ROW_PSI = 3, ROW_SC = 4, ROW_RS = 6, ROWS = SCREEN ? 7 : 6 };  // SC: + parity
   // barrier ids: signal base + parity  (0 is __syncthreads)
   enum { BAR_SC = 1, BAR_XT = 3 };
   __shared__ __align__(16) double2 sh[ROWS][32];
@@ -261,6 +267,11 @@ lane2_rollout_kernel(const RolloutArgs a) {
     *o = is_seg ? make_double2(th, thd) : make_double2(gdx, gdy);
   }
   double sgx = 0.0, sgy = 0.0;
+  // screening state (per environment, replicated on its lanes)
+  const Phys& PS = a.sim;
+  bool alive = true;
+  int viol = 0, frozen = a.H;
+  const double u_ratio = SCREEN ? PS.u_scale / P.u_scale : 1.0, dinv_l = SCREEN ? PS.inv_l - P.inv_l : 0.0;
   double* traj = (a.trajectory && live && seg <= N) ? a.trajectory + e * NO + jpair : nullptr;
   const long long traj_step = a.B * NO;
   double oa = is_seg ? th : gdx, ob = is_seg ? thd : gdy;
@@ -291,6 +302,7 @@ lane2_rollout_kernel(const RolloutArgs a) {
     //      unconditionally, rare tiers under a warp-uniform branch (see lane_rollout.cuh); warp F turns the
     //      angles of step t+1 into the solution rows of step t+1 while M finishes step t ----
     double sN = s, cN = c;
+    const double th_prev = th;
     {
       const double d = P.h * thd;
       const int hi = __double2hiint(d) & 0x7fffffff;
@@ -332,6 +344,18 @@ lane2_rollout_kernel(const RolloutArgs a) {
     const double Ax = fma(-am, s, ttc), Ay = fma(am, c, tts);
     const double Bx = -fma(bp, s, ttc), By = fma(bp, c, -tts);
     const double Bpx = __shfl_up_sync(FULL, Bx, 1, L), Bpy = __shfl_up_sync(FULL, By, 1, L);
+    double taus = 0.0;
+    if (SCREEN) {
+      // the simulator's right-hand side from the same state: its own l (velocities in units of l), kappa, torque scale
+      const double vxs = fma(gdx, dinv_l, vx), vys = fma(gdy, dinv_l, vy);
+      const double vns = fma(vys, c, -vxs * s);
+      taus = fma(PS.kappa, thd, du * u_ratio);
+      const double ams = fma(PS.m2kappa, vns, -taus), bps = fma(PS.m2kappa, vns, taus);
+      const double Axs = fma(-ams, s, ttc), Ays = fma(ams, c, tts);
+      const double Bxs = -fma(bps, s, ttc), Bys = fma(bps, c, -tts);
+      const double Bpxs = __shfl_up_sync(FULL, Bxs, 1, L), Bpys = __shfl_up_sync(FULL, Bys, 1, L);
+      sts2(mine, ROW_RS * kRow, make_double2(Axs - Bpxs, Ays - Bpys));
+    }
     // ---- round 2 ----
     sts2(mine, ROW_PSI * kRow, is_seg ? make_double2(-vn * s, vn * c) : make_double2(0.0, 0.0));
     sts2(mine, ROW_R * kRow, make_double2(Ax - Bpx, Ay - Bpy));
@@ -350,6 +374,19 @@ lane2_rollout_kernel(const RolloutArgs a) {
       acc1 = fma(yrow[j - 1].y, rj.y, acc1);
     }
     const double thdd = acc0 + acc1;
+    if (SCREEN) {
+      double b0 = taus, b1 = 0.0;
+#pragma unroll
+      for (int j = 1; j <= J; ++j) {
+        const double2 rj = lds2(gbase, ROW_RS * kRow + j * 16);
+        b0 = fma(yrow[j - 1].x, rj.x, b0);
+        b1 = fma(yrow[j - 1].y, rj.y, b1);
+      }
+      const double sthd = fma(PS.h, b0 + b1, thd);
+      const double cost = group_max_abs<L>(is_seg ? sthd : 0.0);
+      // unsafe (or NaN): nothing advances, and since observation and policy never change again it never will
+      if (alive && !(cost <= a.sim_thresh)) { alive = false; frozen = t; }
+    }
     // (the shuffle butterfly of lane_rollout.cuh instead of this row: 6-12 % slower here for n = 3 and 5, M's
     // step is a latency chain and the row read hides behind the barrier wait; profiles/r02_summary.md)
     double psx = 0.0, psy = 0.0;
@@ -359,12 +396,20 @@ lane2_rollout_kernel(const RolloutArgs a) {
       psx += pq.x;
       psy += pq.y;
     }
-    gdx = fma(P.h_gdd_c, psx, gdx);
-    gdy = fma(P.h_gdd_c, psy, gdy);
-    thd = fma(P.h, thdd, thd);
-    s = sN; c = cN;
-    sgx += gdx;
-    sgy += gdy;
+    if (!SCREEN || alive) {
+      gdx = fma(P.h_gdd_c, psx, gdx);
+      gdy = fma(P.h_gdd_c, psy, gdy);
+      thd = fma(P.h, thdd, thd);
+      s = sN; c = cN;
+      sgx += gdx;
+      sgy += gdy;
+    } else {
+      th = th_prev;
+    }
+    if (SCREEN) {
+      const double cost = group_max_abs<L>(is_seg ? thd : 0.0);
+      viol += (alive && cost > a.real_thresh) ? 1 : 0;
+    }
     oa = is_seg ? th : gdx;
     ob = is_seg ? thd : gdy;
     if (STATS) {
@@ -391,6 +436,10 @@ lane2_rollout_kernel(const RolloutArgs a) {
     if (a.final_state && seg <= N) {
       *reinterpret_cast<double2*>(a.final_state + e * NO + jpair) =
           is_seg ? make_double2(th, thd) : make_double2(gdx, gdy);
+    }
+    if (SCREEN && seg == 0) {
+      if (a.violations) a.violations[e] = viol;
+      if (a.frozen_at) a.frozen_at[e] = frozen;
     }
   } else if (active && seg == 0) {
     a.returns[e] = __longlong_as_double(0x7ff8000000000000LL);

@@ -85,6 +85,20 @@ __device__ __forceinline__ double group_sum(double v) {
   return v;
 }
 
+// max |v| over the L lanes of an environment, NaN above everything (np.max semantics, as cost_max_abs_thd in
+// kernels.cuh): the sign-stripped bit patterns of doubles order like their magnitudes, so the butterfly runs on the
+// integer pipe; both partners of a level keep the same value, every lane ends with the same result
+template <int L>
+__device__ __forceinline__ double group_max_abs(double v) {
+  long long b = __double_as_longlong(v) & 0x7fffffffffffffffLL;
+#pragma unroll
+  for (int off = 1; off < L; off <<= 1) {
+    const long long o = __shfl_xor_sync(0xffffffffu, b, off);
+    b = o > b ? o : b;
+  }
+  return __longlong_as_double(b);
+}
+
 template <int N, bool LINEAR, bool NORM, bool STATS>
 __global__ void __launch_bounds__(kLaneBlock)
 lane_rollout_kernel(const RolloutArgs a) {

@@ -55,6 +55,42 @@ def test_lane_fixed_action_rollout_matches_oracle(S, O, n, kern):
     np.testing.assert_allclose(r0.returns.cpu().numpy(), r1.returns.cpu().numpy(), rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("kern", ["LANES2", "LANES3"])
+@pytest.mark.parametrize("n", [3, 5, 7])
+def test_lane_per_step_screening_matches_thread_kernel(S, n, kern):
+    """Safe_ARS per-step screening (safe_ars/ars.py:124-153) in the warp-specialised kernels: the simulator's
+    accelerations are a second right-hand side on the same solution rows.  Against the one-thread-per-environment
+    kernel: the step an environment freezes at and its violation count are identical, returns / final states /
+    trajectories (frozen tail repeated) agree to rounding; thresholds are set so that some environments freeze
+    early, some late and some never."""
+    B, H = 40, 200
+    rng = np.random.default_rng(10 * n)
+    real = S.make_params(n=n, l_i=.9, m_i=1.1, k=9.5)
+    sim = S.make_params(n=n, l_i=.93, m_i=1.05, k=9.9)
+    W = _cuda(rng.uniform(-1, 1, (B, (n - 1) * (2 * n + 2))) * 1.5)
+    init = _cuda(rand_states(rng, n, B, scale=0.3))
+    probe = S.ops.rollout(real, H, policies=W, init_state=init, want_trajectory=True, kernel=S.KERNEL_THREAD)
+    peak = probe.trajectory[:, :, 3::2].abs().amax(dim=(0, 2)).cpu().numpy()      # max |thd| per environment
+    thr = float(np.median(peak)) * 0.6
+    kw = dict(policies=W, init_state=init, want_final=True, want_trajectory=True,
+              screen=dict(sim_params=sim, sim_thresh=thr, real_thresh=0.9 * thr))
+    a, b = S.ops.rollout(real, H, kernel=_k(S, kern), **kw), S.ops.rollout(real, H, kernel=S.KERNEL_THREAD, **kw)
+    fa, fb = a.frozen_at.cpu().numpy(), b.frozen_at.cpu().numpy()
+    assert np.array_equal(fa, fb) and np.array_equal(a.violations.cpu().numpy(), b.violations.cpu().numpy())
+    assert (fb < H).sum() >= 5 and (fb == H).sum() >= 5 and len(set(fb.tolist())) >= 5
+    np.testing.assert_allclose(a.returns.cpu().numpy(), b.returns.cpu().numpy(), rtol=1e-9, atol=1e-12)
+    assert rel_err(a.final_state.cpu().numpy(), b.final_state.cpu().numpy()) < 1e-9
+    assert rel_err(a.trajectory.cpu().numpy(), b.trajectory.cpu().numpy()) < 1e-9
+    # a NaN state is unsafe at once (np.max semantics of the cost), its neighbours in the warp are untouched
+    init2 = init.clone()
+    init2[3, 3] = float("nan")
+    c = S.ops.rollout(real, H, kernel=_k(S, kern), **dict(kw, init_state=init2))
+    fc = c.frozen_at.cpu().numpy()
+    assert fc[3] == 0 and np.array_equal(np.delete(fc, 3), np.delete(fa, 3))
+    keep = np.arange(B) != 3
+    assert torch.equal(c.returns[torch.as_tensor(keep)], a.returns[torch.as_tensor(keep)])
+
+
 @pytest.mark.parametrize("kern", LANE_KERNELS)
 @pytest.mark.parametrize("H", [1, 2, 3, 63, 64, 65, 129])
 def test_lane_short_and_odd_horizons(S, kern, H):
@@ -238,6 +274,7 @@ def test_kernel_choice(S):
     assert choice(5, 2048, screen=1) == S.KERNEL_THREAD and choice(5, 2048, clip=1) == S.KERNEL_THREAD
     assert choice(5, 2048, variant=1) == S.KERNEL_THREAD
     assert choice(5, 2048, screen=1, kernel=S.KERNEL_LANES) == -2  # SWM_ERR_UNSUPPORTED
+    assert choice(3, 64, screen=1) == S.KERNEL_LANES2                # per-step screening: warp-specialised kernels only
     assert choice(5, 2048, kernel=S.KERNEL_LANES2) == S.KERNEL_LANES2 and choice(5, 64, clip=1, kernel=S.KERNEL_LANES2) == -2
     with pytest.raises(S.SwimmerLibError):
         S.ops.rollout(S.make_params(n=3), 10, variant=S.RLGLUE, kernel=S.KERNEL_LANES,
