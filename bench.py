@@ -756,6 +756,22 @@ def measure_ars(S, D, dist, device, rank, world, barrier, max_over_ranks, fp64_p
             "agent_iters_per_s": seeds * K3 / dt, "env_steps_per_s": seeds * K3 * 16 * 1000 / dt,
             "ms_per_round": 1e3 * dt / K3, "timing": "host wall clock around %d rounds incl. final sync" % K3}
         del fan
+
+        # Safe_ARS (safe_ars/ars.py: per-step state-constraint screening through a simulator model, V1), 256
+        # directions of the config[3] models: every step of every rollout is first tried on the simulator
+        real = S.make_params(n=3, l_i=0.8, m_i=1.2, k=10.2)
+        sim = S.make_params(n=3, l_i=0.8006, m_i=1.2006, k=10.2006)
+        eng = S.ArsEngine(real, N=256, b=256, alpha=0.0075, nu=0.01, H=1000, semantics=S.ARS_TOPB, seed=3, device=device,
+                          distributed=False, use_graph=True, step_screen=dict(sim_params=sim, sim_thresh=50.0, real_thresh=51.0))
+        K4 = 20
+        t = timed(eng, K4, 5)
+        res["safe_ars per-step screening"] = dict(
+            workload="Safe_ARS (per-step screening: one simulator step before every real step, max|thd| <= threshold), V1, "
+                     "3-segment swimmer, 256 directions (512 rollouts), H=1000, one GPU",
+            iters_per_s=K4 / t, ms_per_iter=1e3 * t / K4, env_steps_per_s=K4 * 512e3 / t, iters_timed=K4,
+            mean_return_last=float(torch.nan_to_num(eng.returns).mean().cpu()),
+            **describe(eng, ", per-step screening as a second right-hand side on the same solution rows"))
+        del eng
     return res
 
 
